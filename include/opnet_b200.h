@@ -1,0 +1,143 @@
+/* libopnet_b200 -- C ABI of the B200-native OPNet temporal-reasoning hot path.
+ *
+ * The reference (ofrikleinfeld/ObjectPermanence) has no FFI layer: its hot path is the
+ * forward()/backward of the nn.Modules in baselines/learned_models.py, whose arithmetic
+ * lives in PyTorch library calls (nn.LSTM, nn.Linear, F.softmax, torch.einsum,
+ * nn.TransformerEncoder).  Each entry point below names the reference call site(s) it
+ * replaces.  The Python host side (objectpermanence_b200/) binds these with ctypes; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous float32 unless stated otherwise
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it:
+ *     no allocation, no host synchronisation (except opn_lstm_status, which says so)
+ *   - return value: OPN_OK (0) or a negative OPN_ERR_*; opn_last_error() gives the text
+ *   - batch-first layouts everywhere: a "row" r = b*T + t
+ *   - sm_100a only; there is no CPU path
+ */
+#ifndef OPNET_B200_H
+#define OPNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OPN_API __attribute__((visibility("default")))
+#else
+#define OPN_API
+#endif
+
+#define OPN_OK 0
+#define OPN_ERR_BAD_ARG (-1)
+#define OPN_ERR_UNSUPPORTED (-2)
+#define OPN_ERR_CUDA (-3)
+#define OPN_ERR_TIMEOUT (-4)
+
+#define OPN_MAX_OBJECTS 15 /* baselines/learned_models.py:13 */
+#define OPN_BOX_FEATURES 6 /* baselines/learned_models.py:21 (OPNet family) */
+
+/* ---- library -------------------------------------------------------------------- */
+OPN_API int opn_version(void);
+OPN_API const char* opn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+OPN_API unsigned long long opn_launch_count(void);
+/* SM count and compute capability of the current device */
+OPN_API int opn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- dense fp32 contraction (CUDA-core FFMA, fp32 accumulate) ---------------------
+ * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N], optional ReLU.
+ *   trans_a == 0: A is [M,K] row-major (lda);  trans_a != 0: A is [K,M] row-major
+ *   trans_b == 0: B is [K,N] row-major (ldb);  trans_b != 0: B is [N,K] row-major
+ *   beta must be 0 or 1; bias may be NULL.
+ *   seg_len > 0 (only with trans_a != 0 && trans_b == 0): the K index is split as
+ *   k = s*seg_len + j and row k of A/B lives at  base + s*seg_stride_{a,b} + j*ld{a,b}
+ *   (used to pair dgates[b,t] with h[b,t-1] without crossing video boundaries).
+ * Replaces: nn.Linear / nn.LSTM input projections and every autograd matmul behind them
+ *   (baselines/learned_models.py:30,33,39,46,47,67,69,70,83,84,100,102,113,116,130,133,
+ *    139,146,149,167,172,178,184,192,195).
+ */
+OPN_API int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int relu,
+              int64_t seg_len, int64_t seg_stride_a, int64_t seg_stride_b, void* stream);
+
+/* ---- persistent LSTM recurrence ---------------------------------------------------
+ * One bias-free, unidirectional LSTM layer with zero initial state, PyTorch gate order
+ * i,f,g,o.  The input projection xproj = x * W_ih^T is computed beforehand (opn_sgemm).
+ * H must be one of 32, 64, 128, 256, 512.
+ * Replaces: the nn.LSTM calls at baselines/learned_models.py:39,46,76,113,146,192 (forward)
+ *   and their autograd backward (baselines/training_main.py:216).
+ *
+ * workspace: opn_lstm_workspace_bytes(B,T,H) bytes, owned by the caller, must stay alive
+ *   until the stream has drained; contents are scratch (step counters, transposed W_hh).
+ */
+OPN_API int64_t opn_lstm_workspace_bytes(int64_t B, int64_t T, int64_t H);
+
+/* forward: xproj [B,T,4H], w_hh [4H,H]  ->  hs [B,T,H]; if gates/cells are non-NULL the
+ * post-activation gates [B,T,4H] (i,f,g,o blocks) and cell states [B,T,H] are stashed for
+ * the backward pass (pass NULL for inference). */
+OPN_API int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj, const float* w_hh, float* hs, float* gates,
+                 float* cells, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* backward recurrence: dh_out [B,T,H] is dLoss/dh from the consumers of hs.  Writes
+ * dgates [B,T,4H] = dLoss/d(pre-activation gates).  Parameter and input gradients are
+ * time-parallel contractions of dgates (opn_sgemm):
+ *   dW_ih = dgates^T x ; dW_hh = sum_t dgates[:,t]^T hs[:,t-1] ; dx = dgates W_ih. */
+OPN_API int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* cells,
+                 const float* dh_out, float* dgates, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* SYNCHRONISES the device.  Reads back the status word the persistent kernels leave in
+ * `workspace`: OPN_OK, or OPN_ERR_TIMEOUT if an inter-CTA wait expired (detail words in
+ * info[0..2] if info != NULL).  For tests and debugging. */
+OPN_API int opn_lstm_status(const void* workspace, uint32_t* info);
+
+/* ---- OPNet "who to track" stage ---------------------------------------------------
+ * forward (baselines/learned_models.py:40-43,50):
+ *   logits = hs1 * w_pred^T            [B,T,15]
+ *   probs  = softmax(logits, -1)
+ *   frames_boxes[b,t,:] = sum_o probs[b,t,o] * boxes[b,t,o,:]        [B,T,6]
+ *   logits_bpt = logits.permute(0,2,1).contiguous()                  [B,15,T]
+ */
+OPN_API int opn_wtt_fwd(int64_t B, int64_t T, int64_t H1, const float* boxes, const float* hs1, const float* w_pred,
+                float* logits_bpt, float* probs, float* frames_boxes, void* stream);
+/* backward: d_frames_boxes [B,T,6], optional d_logits_bpt [B,15,T] (NULL = no gradient
+ * arrives on the logits output, as in baselines/training_main.py:186-216) ->
+ *   d_logits [B,T,15] (row layout, for dW_pred = d_logits^T hs1 via opn_sgemm),
+ *   d_hs1 [B,T,H1]. */
+OPN_API int opn_wtt_bwd(int64_t B, int64_t T, int64_t H1, const float* boxes, const float* probs, const float* w_pred,
+                const float* d_frames_boxes, const float* d_logits_bpt, float* d_logits, float* d_hs1,
+                void* stream);
+
+/* ---- element-wise / row-wise helpers (transformer_lstm encoder, MLP variant) -------- */
+/* dy[i] = (y[i] > 0) ? dy[i] : 0   (ReLU backward, in place on dy) */
+OPN_API int opn_relu_bwd(int64_t n, const float* y, float* dy, void* stream);
+/* out[c] (+)= sum_r x[r*ld + c]   (bias gradients) */
+OPN_API int opn_colsum(int64_t rows, int64_t cols, const float* x, int64_t ld, float* out, int accumulate, void* stream);
+/* row softmax in place over x [rows, cols] (ld); scale applied to the logits first */
+OPN_API int opn_softmax_rows(int64_t rows, int64_t cols, float* x, int64_t ld, float scale, void* stream);
+/* softmax backward in place: dp <- scale * p * (dp - sum_j p_j dp_j) */
+OPN_API int opn_softmax_rows_bwd(int64_t rows, int64_t cols, const float* p, float* dp, int64_t ld, float scale, void* stream);
+/* y = LayerNorm(x + res) * w + b over the last dim D (res may be NULL).  Stashes the
+ * normalised activations xhat [rows,D] and rstd [rows] for the backward pass.
+ * Replaces norm1/norm2 of nn.TransformerEncoderLayer (baselines/learned_models.py:166). */
+OPN_API int opn_layernorm_fwd(int64_t rows, int64_t D, const float* x, const float* res, const float* w, const float* b,
+                      float eps, float* y, float* xhat, float* rstd, void* stream);
+/* backward: dx [rows,D] (gradient w.r.t. the sum x+res); dw, db [D] are accumulated (+=) */
+OPN_API int opn_layernorm_bwd(int64_t rows, int64_t D, const float* xhat, const float* rstd, const float* w, const float* dy,
+                      float* dx, float* dw, float* db, void* stream);
+/* out = a + b */
+OPN_API int opn_add(int64_t n, const float* a, const float* b, float* out, void* stream);
+
+/* ---- training loss (baselines/training_main.py:192-210) ---------------------------
+ * loss = mean(|y - labels| [* mask]) [+ 0.5 * mean_t ||y[t+1]-y[t]||_2]  and its gradient
+ * dy, in one launch.  mask (uint8 [B,T,4]) may be NULL; consistency != 0 adds the second
+ * term (the *_no_labels models).  loss_out: 3 floats {total, prediction, consistency}. */
+OPN_API int opn_loss_fwd_bwd(int64_t B, int64_t T, const float* y, const float* labels, const uint8_t* mask, int consistency,
+                     float* loss_out, float* dy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPNET_B200_H */

@@ -1,0 +1,39 @@
+// Library-level entry points and host-side error plumbing of libopnet_b200.
+#include <stdarg.h>
+#include <string.h>
+
+#include "opn_common.cuh"
+
+namespace opn {
+
+static thread_local char g_error[512] = "";
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return OPN_ERR_CUDA;
+}
+
+}  // namespace opn
+
+extern "C" int opn_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" const char* opn_last_error(void) { return opn::g_error; }
+
+extern "C" unsigned long long opn_launch_count(void) { return opn::g_launch_count; }
+
+extern "C" int opn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    OPN_CUDA(cudaGetDevice(&dev));
+    if (sm_count) OPN_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major) OPN_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_minor) OPN_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return OPN_OK;
+}

@@ -1,0 +1,425 @@
+"""Host-side operators: torch.autograd.Functions whose forward and backward enqueue
+hand-written sm_100a kernels through the C ABI (include/opnet_b200.h).
+
+PyTorch is plumbing here: it owns device memory (torch.empty), the current stream and the
+autograd graph.  No arithmetic on the hot path is done by a PyTorch kernel, and there is no
+CPU path -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import os
+from ctypes import c_uint32
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DEBUG_SYNC = os.environ.get("OPN_DEBUG_SYNC", "0") not in ("", "0")
+
+
+def set_debug_sync(flag: bool) -> None:
+    """When on, every persistent-LSTM launch is followed by a device sync + status check."""
+    global _DEBUG_SYNC
+    _DEBUG_SYNC = bool(flag)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "objectpermanence_b200 runs on CUDA (sm_100a) only: there is no CPU path. Move the module and its "
+                "inputs to a B200 (`.to('cuda')`).")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"objectpermanence_b200 expects float32 tensors, got {t.dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------
+# raw kernels wrappers (no autograd)
+# ------------------------------------------------------------------------------------------
+def sgemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a: bool, trans_b: bool, M: int, N: int,
+          K: int, lda: int, ldb: int, ldc: int, alpha: float = 1.0, beta: float = 0.0,
+          bias: Optional[torch.Tensor] = None, relu: bool = False, seg: Optional[Tuple[int, int, int]] = None,
+          a_off: int = 0, b_off: int = 0, c_off: int = 0) -> None:
+    """out = alpha * op(a) op(b) + beta * out + bias.  Offsets are in elements."""
+    if K == 0:
+        if beta == 0.0:
+            out.zero_()
+        return
+    seg_len, seg_sa, seg_sb = seg if seg is not None else (0, 0, 0)
+    rc = _lib.load().opn_sgemm(int(trans_a), int(trans_b), M, N, K, alpha, a.data_ptr() + 4 * a_off, lda,
+                               b.data_ptr() + 4 * b_off, ldb, beta, out.data_ptr() + 4 * c_off, ldc, _ptr(bias),
+                               int(relu), seg_len, seg_sa, seg_sb, _stream())
+    _lib.check(rc, "opn_sgemm")
+
+
+def _lstm_workspace(B: int, T: int, H: int, device) -> torch.Tensor:
+    n = _lib.load().opn_lstm_workspace_bytes(B, T, H)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def _lstm_check(ws: torch.Tensor, what: str) -> None:
+    if _DEBUG_SYNC:
+        info = (c_uint32 * 3)()
+        rc = _lib.load().opn_lstm_status(ws.data_ptr(), info)
+        _lib.check(rc, what)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T (+ bias) (ReLU).  x [..., K] contiguous, W [N, K].  nn.Linear call sites of
+    baselines/learned_models.py (:30,:33,:67,:69,:70,:102,:130,:133,:167,:172)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool):
+        _require_cuda(x, weight, bias)
+        x = x.contiguous()
+        weight = weight.contiguous()
+        K = x.shape[-1]
+        N = weight.shape[0]
+        M = x.numel() // K
+        y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+        sgemm(x, weight, y, trans_a=False, trans_b=True, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, bias=bias, relu=relu)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.has_bias = bias is not None
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        K = x.shape[-1]
+        N = weight.shape[0]
+        M = x.numel() // K
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = dy.clone()
+            _lib.check(_lib.load().opn_relu_bwd(dy.numel(), y.data_ptr(), dy.data_ptr(), _stream()), "opn_relu_bwd")
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            sgemm(dy, weight, dx, trans_a=False, trans_b=False, M=M, N=K, K=N, lda=N, ldb=K, ldc=K)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            sgemm(dy, x, dw, trans_a=True, trans_b=False, M=N, N=K, K=M, lda=N, ldb=K, ldc=K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(N, device=x.device, dtype=torch.float32)
+            _lib.check(_lib.load().opn_colsum(M, N, dy.data_ptr(), N, db.data_ptr(), 0, _stream()), "opn_colsum")
+        return dx, dw, db, None
+
+
+class SlotLinearReluFn(torch.autograd.Function):
+    """relu(boxes[:, :, slot, :] W^T) without materialising the slice: the snitch-slot rows of
+    boxes [B,T,15,F] are read in place with a row stride of 15*F.  transformer_lstm keeps only
+    slot 0 of the encoder output (baselines/learned_models.py:178,185); the other 14 slots never
+    reach the output or any gradient, so they are not computed."""
+
+    @staticmethod
+    def forward(ctx, boxes, weight, slot: int):
+        _require_cuda(boxes, weight)
+        boxes = boxes.contiguous()
+        weight = weight.contiguous()
+        B, T, NO, F = boxes.shape
+        D = weight.shape[0]
+        y = torch.empty(B, T, D, device=boxes.device, dtype=torch.float32)
+        sgemm(boxes, weight, y, trans_a=False, trans_b=True, M=B * T, N=D, K=F, lda=NO * F, ldb=F, ldc=D, relu=True,
+              a_off=slot * F)
+        ctx.save_for_backward(boxes, weight, y)
+        ctx.slot = slot
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        boxes, weight, y = ctx.saved_tensors
+        B, T, NO, F = boxes.shape
+        D = weight.shape[0]
+        dy = dy.contiguous().clone()
+        _lib.check(_lib.load().opn_relu_bwd(dy.numel(), y.data_ptr(), dy.data_ptr(), _stream()), "opn_relu_bwd")
+        dw = torch.empty_like(weight)
+        sgemm(dy, boxes, dw, trans_a=True, trans_b=False, M=D, N=F, K=B * T, lda=D, ldb=NO * F, ldc=F,
+              b_off=ctx.slot * F)
+        return None, dw, None
+
+
+class LstmLayerFn(torch.autograd.Function):
+    """One bias-free LSTM layer (batch-first, zero initial state): the persistent recurrence
+    kernels plus the time-parallel input projection / gradient contractions."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh):
+        _require_cuda(x, w_ih, w_hh)
+        x = x.contiguous()
+        w_ih = w_ih.contiguous()
+        w_hh = w_hh.contiguous()
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        lib = _lib.load()
+        dev = x.device
+        xproj = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
+        sgemm(x, w_ih, xproj, trans_a=False, trans_b=True, M=B * T, N=4 * H, K=I, lda=I, ldb=I, ldc=4 * H)
+        hs = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)  # all False under torch.no_grad(): inference skips the stash
+        gates = cells = None
+        if need_grad:
+            gates = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
+            cells = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+        ws = _lstm_workspace(B, T, H, dev)
+        rc = lib.opn_lstm_fwd(B, T, H, xproj.data_ptr(), w_hh.data_ptr(), hs.data_ptr(), _ptr(gates), _ptr(cells),
+                              ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "opn_lstm_fwd")
+        _lstm_check(ws, "opn_lstm_fwd")
+        if need_grad:
+            ctx.save_for_backward(x, w_ih, w_hh, hs, gates, cells)
+        return hs
+
+    @staticmethod
+    def backward(ctx, dhs):
+        x, w_ih, w_hh, hs, gates, cells = ctx.saved_tensors
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        lib = _lib.load()
+        dev = x.device
+        dhs = dhs.contiguous()
+        dgates = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
+        ws = _lstm_workspace(B, T, H, dev)
+        rc = lib.opn_lstm_bwd(B, T, H, w_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dhs.data_ptr(),
+                              dgates.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "opn_lstm_bwd")
+        _lstm_check(ws, "opn_lstm_bwd")
+        dx = dw_ih = dw_hh = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            sgemm(dgates, w_ih, dx, trans_a=False, trans_b=False, M=B * T, N=I, K=4 * H, lda=4 * H, ldb=I, ldc=I)
+        if ctx.needs_input_grad[1]:
+            dw_ih = torch.empty_like(w_ih)
+            sgemm(dgates, x, dw_ih, trans_a=True, trans_b=False, M=4 * H, N=I, K=B * T, lda=4 * H, ldb=I, ldc=I)
+        if ctx.needs_input_grad[2]:
+            dw_hh = torch.empty_like(w_hh)
+            if T > 1:
+                # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1]: K runs over B segments of T-1 rows
+                sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B * (T - 1), lda=4 * H, ldb=H,
+                      ldc=H, seg=(T - 1, T * 4 * H, T * H), a_off=4 * H)
+            else:
+                dw_hh.zero_()
+        return dx, dw_ih, dw_hh
+
+
+class WhoToTrackFn(torch.autograd.Function):
+    """OPNet's soft object selection (baselines/learned_models.py:40-43,50)."""
+
+    @staticmethod
+    def forward(ctx, boxes, hs1, w_pred):
+        _require_cuda(boxes, hs1, w_pred)
+        boxes = boxes.contiguous()
+        hs1 = hs1.contiguous()
+        w_pred = w_pred.contiguous()
+        B, T, NO, F = boxes.shape
+        if NO != 15 or F != 6 or w_pred.shape[0] != 15:
+            raise RuntimeError("who-to-track expects boxes [B,T,15,6] and object_to_track_pred_dim == 15 "
+                               "(the reference einsum requires it, baselines/learned_models.py:43)")
+        H1 = hs1.shape[-1]
+        dev = boxes.device
+        logits = torch.empty(B, 15, T, device=dev, dtype=torch.float32)
+        probs = torch.empty(B, T, 15, device=dev, dtype=torch.float32)
+        fb = torch.empty(B, T, 6, device=dev, dtype=torch.float32)
+        rc = _lib.load().opn_wtt_fwd(B, T, H1, boxes.data_ptr(), hs1.data_ptr(), w_pred.data_ptr(), logits.data_ptr(),
+                                     probs.data_ptr(), fb.data_ptr(), _stream())
+        _lib.check(rc, "opn_wtt_fwd")
+        ctx.save_for_backward(boxes, hs1, w_pred, probs)
+        return fb, logits
+
+    @staticmethod
+    def backward(ctx, dfb, dlogits):
+        boxes, hs1, w_pred, probs = ctx.saved_tensors
+        B, T, NO, F = boxes.shape
+        H1 = hs1.shape[-1]
+        dev = boxes.device
+        if dfb is None:
+            dfb = torch.zeros(B, T, 6, device=dev, dtype=torch.float32)
+        dfb = dfb.contiguous()
+        dl_up = dlogits.contiguous() if dlogits is not None else None
+        dl = torch.empty(B, T, 15, device=dev, dtype=torch.float32)
+        dhs1 = torch.empty_like(hs1)
+        rc = _lib.load().opn_wtt_bwd(B, T, H1, boxes.data_ptr(), probs.data_ptr(), w_pred.data_ptr(), dfb.data_ptr(),
+                                     _ptr(dl_up), dl.data_ptr(), dhs1.data_ptr(), _stream())
+        _lib.check(rc, "opn_wtt_bwd")
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty_like(w_pred)
+            sgemm(dl, hs1, dw, trans_a=True, trans_b=False, M=15, N=H1, K=B * T, lda=15, ldb=H1, ldc=H1)
+        return None, dhs1, dw
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """LayerNorm(x + res) (post-norm residual blocks of nn.TransformerEncoderLayer)."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, eps: float):
+        _require_cuda(x, res, weight, bias)
+        x = x.contiguous()
+        res = res.contiguous()
+        D = x.shape[-1]
+        rows = x.numel() // D
+        y = torch.empty_like(x)
+        xhat = torch.empty_like(x)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rc = _lib.load().opn_layernorm_fwd(rows, D, x.data_ptr(), res.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                           eps, y.data_ptr(), xhat.data_ptr(), rstd.data_ptr(), _stream())
+        _lib.check(rc, "opn_layernorm_fwd")
+        ctx.save_for_backward(xhat, rstd, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhat, rstd, weight = ctx.saved_tensors
+        D = xhat.shape[-1]
+        rows = xhat.numel() // D
+        dy = dy.contiguous()
+        dx = torch.empty_like(xhat)
+        dw = torch.zeros_like(weight)
+        db = torch.zeros_like(weight)
+        rc = _lib.load().opn_layernorm_bwd(rows, D, xhat.data_ptr(), rstd.data_ptr(), weight.data_ptr(), dy.data_ptr(),
+                                           dx.data_ptr(), dw.data_ptr(), db.data_ptr(), _stream())
+        _lib.check(rc, "opn_layernorm_bwd")
+        return dx, dx, dw, db, None
+
+
+class SelfAttentionFn(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(d)) V per head over ONE sequence of S rows.
+
+    qkv [S, 3D] packed q|k|v as produced by in_proj (nn.MultiheadAttention ordering), nhead heads
+    of d = D/nhead.  The sequence axis of the reference is B*T (baselines/learned_models.py:183-184
+    hands a (B*T, 15, D) tensor to a sequence-first encoder), so S = B*T here.  The score matrix is
+    materialised per head in HBM ([S,S] fp32; 369 MB at S = 9600) and kept for the backward pass."""
+
+    @staticmethod
+    def forward(ctx, qkv, nhead: int):
+        _require_cuda(qkv)
+        qkv = qkv.contiguous()
+        S, D3 = qkv.shape
+        D = D3 // 3
+        d = D // nhead
+        scale = 1.0 / (d ** 0.5)
+        dev = qkv.device
+        lib = _lib.load()
+        ctx_out = torch.empty(S, D, device=dev, dtype=torch.float32)
+        probs = torch.empty(nhead, S, S, device=dev, dtype=torch.float32)
+        for h in range(nhead):
+            p = probs[h]
+            # scores = q_h k_h^T
+            sgemm(qkv, qkv, p, trans_a=False, trans_b=True, M=S, N=S, K=d, lda=D3, ldb=D3, ldc=S, a_off=h * d,
+                  b_off=D + h * d)
+            _lib.check(lib.opn_softmax_rows(S, S, p.data_ptr(), S, scale, _stream()), "opn_softmax_rows")
+            # ctx_h = P v_h
+            sgemm(p, qkv, ctx_out, trans_a=False, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D3, ldc=D,
+                  b_off=2 * D + h * d, c_off=h * d)
+        ctx.save_for_backward(qkv, probs)
+        ctx.nhead = nhead
+        return ctx_out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, probs = ctx.saved_tensors
+        nhead = ctx.nhead
+        S, D3 = qkv.shape
+        D = D3 // 3
+        d = D // nhead
+        scale = 1.0 / (d ** 0.5)
+        dev = qkv.device
+        lib = _lib.load()
+        dctx = dctx.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dp = torch.empty(S, S, device=dev, dtype=torch.float32)
+        for h in range(nhead):
+            p = probs[h]
+            # dV_h = P^T dctx_h
+            sgemm(p, dctx, dqkv, trans_a=True, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D, ldc=D3, b_off=h * d,
+                  c_off=2 * D + h * d)
+            # dP = dctx_h V_h^T
+            sgemm(dctx, qkv, dp, trans_a=False, trans_b=True, M=S, N=S, K=d, lda=D, ldb=D3, ldc=S, a_off=h * d,
+                  b_off=2 * D + h * d)
+            # dS = scale * P * (dP - rowsum(P dP))
+            _lib.check(lib.opn_softmax_rows_bwd(S, S, p.data_ptr(), dp.data_ptr(), S, scale, _stream()),
+                       "opn_softmax_rows_bwd")
+            # dQ_h = dS K_h ; dK_h = dS^T Q_h
+            sgemm(dp, qkv, dqkv, trans_a=False, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D3, ldc=D3, b_off=D + h * d,
+                  c_off=h * d)
+            sgemm(dp, qkv, dqkv, trans_a=True, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D3, ldc=D3, b_off=h * d,
+                  c_off=D + h * d)
+        return dqkv, None
+
+
+class TrainingLossFn(torch.autograd.Function):
+    """The loss of baselines/training_main.py:192-210 and its gradient in one launch.
+    Returns a 3-vector (total, prediction, consistency); only `total` carries gradient."""
+
+    @staticmethod
+    def forward(ctx, y, labels, mask, no_labels: bool):
+        _require_cuda(y, labels)
+        y = y.contiguous()
+        labels = labels.contiguous()
+        B, T, C = y.shape
+        if C != 4:
+            raise RuntimeError("training loss expects [B,T,4] predictions")
+        m = None
+        if no_labels:
+            if mask is None:
+                raise RuntimeError("*_no_labels models need the visibility mask")
+            m = mask.to(torch.uint8).contiguous()
+        out = torch.empty(3, device=y.device, dtype=torch.float32)
+        dy = torch.empty_like(y)
+        rc = _lib.load().opn_loss_fwd_bwd(B, T, y.data_ptr(), labels.data_ptr(), _ptr(m), int(no_labels),
+                                          out.data_ptr(), dy.data_ptr(), _stream())
+        _lib.check(rc, "opn_loss_fwd_bwd")
+        ctx.save_for_backward(dy)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (dy,) = ctx.saved_tensors
+        # d total / dy was produced by the forward launch; scale by the incoming scalar
+        return dy * dout[0], None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# functional front-ends
+# ------------------------------------------------------------------------------------------
+def linear(x, weight, bias=None, relu: bool = False):
+    return LinearFn.apply(x, weight, bias, relu)
+
+
+def lstm_layer(x, w_ih, w_hh):
+    return LstmLayerFn.apply(x, w_ih, w_hh)
+
+
+def who_to_track(boxes, hs1, w_pred):
+    return WhoToTrackFn.apply(boxes, hs1, w_pred)
+
+
+def add_layer_norm(x, res, weight, bias, eps: float = 1e-5):
+    return AddLayerNormFn.apply(x, res, weight, bias, eps)
+
+
+def self_attention(qkv, nhead: int):
+    return SelfAttentionFn.apply(qkv, nhead)
+
+
+def slot_linear_relu(boxes, weight, slot: int = 0):
+    return SlotLinearReluFn.apply(boxes, weight, slot)
+
+
+def training_loss(y, labels, mask=None, no_labels: bool = False):
+    """(total, prediction, consistency) as a 3-vector; differentiate `[0]`."""
+    return TrainingLossFn.apply(y, labels, mask, no_labels)
