@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: videos/sec of OPNet forward + loss + backward on synthetic
+[B=32 per GPU, T=300, N=15, F=6] fp32 inputs (BASELINE.json configs[1]; shipped JSON hidden sizes
+H1=256, H2=512), one process per GPU, gradients all-reduced once per step when N > 1.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line on rank 0 (contract in the task prompt):
+  value     whole-job videos/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same through objectpermanence_b200.training.TrainingStep with pinned HOST buffers
+            (H2D of boxes+labels and a D2H read of the loss inside the timed region)
+  roofline  the dominant kernel (the persistent LSTM2 backward recurrence) against measured HBM peak
+  cpu_baseline  the oracle port of the reference path on the host cores, bounded sample
+`--impl reference` times only that CPU port (the reference is pure Python on PyTorch and is not
+present on the GPU box; oracle/opnet_oracle.py restates it and calls the same fused CPU LSTM
+the reference's nn.LSTM dispatches to).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np
+import torch
+
+OPNET_CFG = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+B_PER_GPU, T, NOBJ, FEAT = 32, 300, 15, 6
+METRIC = "videos/sec OPNet fwd+bwd [B,T=300,N=15,h=256]"
+UNIT = "videos/s"
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps: int, warmup: int, batch: int):
+    """fwd + L1 loss + bwd of the OPNet restatement on the host cores (all threads)."""
+    from oracle import opnet_oracle as oracle
+    from objectpermanence_b200.synthetic import make_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    boxes_np, labels_np, _ = make_batch(batch, T, FEAT, seed=1234)
+    boxes, labels = torch.from_numpy(boxes_np), torch.from_numpy(labels_np)
+    params = {k: v.clone().requires_grad_(True) for k, v in oracle.init_params("opnet", OPNET_CFG, seed=0).items()}
+    times = []
+    for it in range(warmup + steps):
+        for v in params.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        y, _ = oracle.opnet_forward(params, boxes, fast=True)
+        loss = oracle.training_loss(y, labels)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit without work
+    steps = max(1, args.steps)
+    times = cpu_reference_steps(steps, max(1, min(args.warmup, 2)), B_PER_GPU)
+    sec = sum(times) / len(times)
+    value = B_PER_GPU / sec
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "opnet configs/opnet_model_config.json [B=32,T=300,N=15,F=6] H1=256 H2=512, "
+                               "fwd + L1 loss + bwd on CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} full steps of the [32,300,15,6] workload (oracle port, torch fused CPU LSTM)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from objectpermanence_b200 import _lib, ops
+    from objectpermanence_b200.data_parallel import (FlatGradAllReducer, broadcast_parameters,
+                                                     init_process_group_from_env)
+    from objectpermanence_b200.models_factory import ModelsFactory
+    from objectpermanence_b200.synthetic import make_batch
+    from objectpermanence_b200.training import TrainingStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    world = init_process_group_from_env("nccl")
+    rank = dist.get_rank() if world > 1 else 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+
+    torch.manual_seed(0)
+    model = ModelsFactory.get_model("opnet", OPNET_CFG).to(dev).train()
+    broadcast_parameters(model.parameters())
+    reducer = FlatGradAllReducer(model.parameters()) if world > 1 else None
+    step = TrainingStep(model, "opnet", reducer=reducer)
+
+    boxes_np, labels_np, _ = make_batch(B_PER_GPU, T, FEAT, seed=1234 + rank)
+    boxes_h = torch.from_numpy(boxes_np).pin_memory()
+    labels_h = torch.from_numpy(labels_np).pin_memory()
+    boxes_d, labels_d = boxes_h.to(dev), labels_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        launches0 = _lib.launch_count()
+        wall0 = time.time()
+        for i in range(steps):
+            flush.fill_(float(i))          # untimed L2 flush between iterations
+            starts[i].record()
+            fn()
+            ends[i].record()
+        barrier()
+        wall1 = time.time()
+        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, _lib.launch_count() - launches0, wall0, wall1
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+
+    # (1) device-resident inputs
+    total_ms, launches, w0, w1 = timed(lambda: step.forward_backward(boxes_d, labels_d), args.steps, args.warmup)
+    # (2) end to end from pinned host buffers through the public step API
+    e2e_ms, _, _, w2 = timed(lambda: step(boxes_h, labels_h), args.steps, max(1, args.warmup // 2))
+    clocks = sampler.stop(w0, w2) if sampler else None
+
+    ms_per_step = total_ms / args.steps
+    value = world * B_PER_GPU / (ms_per_step * 1e-3)
+    e2e_value = world * B_PER_GPU / (e2e_ms / args.steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel, timed alone on its launching stream
+    peaks, peak_src = measured_peaks()
+    H1, H2 = OPNET_CFG["object_to_track_hidden_dim"], OPNET_CFG["videos_hidden_dim"]
+    kern = {}
+    with torch.no_grad():
+        for name, H in (("lstm_fwd_h512", H2), ("lstm_bwd_h512", H2), ("lstm_fwd_h256", H1), ("lstm_bwd_h256", H1)):
+            xp = torch.randn(B_PER_GPU, T, 4 * H, device=dev) * 0.5
+            whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / (H ** 0.5)
+            hs = torch.empty(B_PER_GPU, T, H, device=dev)
+            gates = torch.empty(B_PER_GPU, T, 4 * H, device=dev)
+            cells = torch.empty(B_PER_GPU, T, H, device=dev)
+            dh = torch.randn(B_PER_GPU, T, H, device=dev) * 0.01
+            dg = torch.empty(B_PER_GPU, T, 4 * H, device=dev)
+            ws = torch.empty(_lib.load().opn_lstm_workspace_bytes(B_PER_GPU, T, H), dtype=torch.uint8, device=dev)
+            lib = _lib.load()
+            s = torch.cuda.current_stream().cuda_stream
+
+            def fwd():
+                _lib.check(lib.opn_lstm_fwd(B_PER_GPU, T, H, xp.data_ptr(), whh.data_ptr(), hs.data_ptr(),
+                                            gates.data_ptr(), cells.data_ptr(), ws.data_ptr(), ws.numel(), s))
+
+            def bwd():
+                _lib.check(lib.opn_lstm_bwd(B_PER_GPU, T, H, whh.data_ptr(), gates.data_ptr(), cells.data_ptr(),
+                                            dh.data_ptr(), dg.data_ptr(), ws.data_ptr(), ws.numel(), s))
+
+            fwd()
+            fn = fwd if "fwd" in name else bwd
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            ms = 0.0
+            for _ in range(reps):
+                flush.fill_(1.0)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1)
+            ms /= reps
+            rows = B_PER_GPU * T
+            if "fwd" in name:   # read xproj + W_hh, write hs + gates + cells
+                alg = 4 * (rows * (4 * H + H + 4 * H + H) + 4 * H * H)
+            else:               # read gates + cells + dh_out + W_hh, write dgates
+                alg = 4 * (rows * (4 * H + H + H + 4 * H) + 4 * H * H)
+            kern[name] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9,
+                          "us_per_step": ms * 1e3 / T,
+                          "ffma_tflops": 2.0 * rows * 4 * H * H / (ms * 1e-3) / 1e12}
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    hbm_peak = float(peaks["hbm_gbs"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kern[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "note": "recurrence is FP32-FFMA / step-latency bound (arithmetic intensity ~260 FLOP/B), "
+                        "see DESIGN.md section 5; per-kernel detail in 'kernels'",
+                "whole_step_algorithmic_gbs": (31700.0 * B_PER_GPU * T + 17.05e6) / (ms_per_step * 1e-3) / 1e9}
+
+    # CPU baseline: bounded sample of the same workload on the host cores
+    cpu_times = cpu_reference_steps(steps=3, warmup=1, batch=B_PER_GPU)
+    cpu_value = B_PER_GPU / (sum(cpu_times) / len(cpu_times))
+
+    h2d = boxes_h.numel() * 4 + labels_h.numel() * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "opnet configs/opnet_model_config.json [B=32 per GPU,T=300,N=15,F=6] H1=256 H2=512, "
+                               "zero_grad + fwd + L1 loss + bwd" + (" + 1 NCCL grad all-reduce" if world > 1 else ""),
+                   "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
+                   "l2": "256 MB buffer written between timed iterations (untimed)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kern,
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": "3 full steps of the [32,300,15,6] workload (oracle port, torch fused CPU LSTM)"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        args.warmup = max(3, args.warmup)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+"""GPU: each C-ABI kernel against a CPU fp64 restatement (oracle / plain torch CPU math)."""
+import math
+
+import pytest
+import torch
+
+from objectpermanence_b200 import _lib, ops
+from oracle import opnet_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * scale).float()
+
+
+# ---- sgemm --------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (130, 70, 33), (257, 129, 64), (96, 4, 512), (300, 2048, 6),
+                                    (2048, 6, 1200), (64, 512, 4)])
+def test_sgemm_shapes(cuda_device, ta, tb, M, N, K):
+    a = _rand((K, M) if ta else (M, K), 1)
+    b = _rand((N, K) if tb else (K, N), 2)
+    ref = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    out = torch.full((M, N), float("nan"), device=cuda_device)
+    ops.sgemm(a.to(cuda_device), b.to(cuda_device), out, trans_a=ta, trans_b=tb, M=M, N=N, K=K,
+              lda=a.shape[1], ldb=b.shape[1], ldc=N)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 1e-5 * max(1.0, math.sqrt(K)), err
+
+
+def test_sgemm_epilogue_and_split_k(cuda_device):
+    M, N, K = 40, 24, 4096  # small grid + long K -> split-K with atomics
+    a, b, bias, c0 = _rand((K, M), 3), _rand((K, N), 4), _rand((N,), 5), _rand((M, N), 6)
+    out = c0.clone().to(cuda_device)
+    ops.sgemm(a.to(cuda_device), b.to(cuda_device), out, trans_a=True, trans_b=False, M=M, N=N, K=K, lda=M, ldb=N,
+              ldc=N, alpha=0.5, beta=1.0, bias=bias.to(cuda_device))
+    ref = 0.5 * (a.double().t() @ b.double()) + c0.double() + bias.double()
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-4
+    # relu + bias, no split
+    x, w = _rand((50, 20), 7), _rand((30, 20), 8)
+    out2 = torch.empty(50, 30, device=cuda_device)
+    ops.sgemm(x.to(cuda_device), w.to(cuda_device), out2, trans_a=False, trans_b=True, M=50, N=30, K=20, lda=20,
+              ldb=20, ldc=30, bias=_rand((30,), 9).to(cuda_device), relu=True)
+    ref2 = torch.relu(x.double() @ w.double().t() + _rand((30,), 9).double())
+    assert (out2.cpu().double() - ref2).abs().max().item() <= 1e-5
+
+
+def test_sgemm_segmented_k_pairs_gates_with_previous_hidden(cuda_device):
+    B, T, G, H = 3, 7, 24, 8
+    dg, hs = _rand((B, T, G), 10), _rand((B, T, H), 11)
+    ref = torch.einsum("btg,bth->gh", dg[:, 1:].double(), hs[:, :-1].double())
+    out = torch.empty(G, H, device=cuda_device)
+    ops.sgemm(dg.to(cuda_device), hs.to(cuda_device), out, trans_a=True, trans_b=False, M=G, N=H, K=B * (T - 1),
+              lda=G, ldb=H, ldc=H, seg=(T - 1, T * G, T * H), a_off=G)
+    assert (out.cpu().double() - ref).abs().max().item() <= 1e-5
+
+
+# ---- persistent LSTM ------------------------------------------------------------------------
+def _lstm_case(B, T, I, H, seed, scale=1.0):
+    x = _rand((B, T, I), seed, 1.0)
+    w_ih = _rand((4 * H, I), seed + 1, scale / math.sqrt(H))
+    w_hh = _rand((4 * H, H), seed + 2, scale / math.sqrt(H))
+    dh = _rand((B, T, H), seed + 3, 1.0)
+    return x, w_ih, w_hh, dh
+
+
+@pytest.mark.parametrize("H", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 8), (8, 5), (11, 17), (32, 12)])
+def test_lstm_layer_forward_backward(cuda_device, H, B, T):
+    I = 6 if H != 64 else 75
+    x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=100 * H + B + T)
+    xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
+    ref = oracle.lstm_layer(xr, wir, whr)
+    ref.backward(dh.double())
+
+    xg, wig, whg = [t.to(cuda_device).requires_grad_(True) for t in (x, w_ih, w_hh)]
+    out = ops.lstm_layer(xg, wig, whg)
+    out.backward(dh.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5
+    for name, got, want in (("dx", xg.grad, xr.grad), ("dw_ih", wig.grad, wir.grad), ("dw_hh", whg.grad, whr.grad)):
+        scale = max(1.0, want.abs().max().item())
+        err = (got.cpu().double() - want).abs().max().item()
+        assert err <= 5e-5 * scale, (name, err, scale)
+
+
+def test_lstm_saturating_weights(cuda_device):
+    B, T, I, H = 9, 40, 90, 256
+    x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=7, scale=8.0)
+    xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
+    ref = oracle.lstm_layer(xr, wir, whr)
+    ref.backward(dh.double())
+    xg, wig, whg = [t.to(cuda_device).requires_grad_(True) for t in (x, w_ih, w_hh)]
+    out = ops.lstm_layer(xg, wig, whg)
+    out.backward(dh.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-4
+    for got, want in ((xg.grad, xr.grad), (wig.grad, wir.grad), (whg.grad, whr.grad)):
+        assert (got.cpu().double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+def test_lstm_inference_mode_skips_stash(cuda_device):
+    x, w_ih, w_hh, _ = _lstm_case(4, 9, 6, 128, seed=21)
+    ref = oracle.lstm_layer(x.double(), w_ih.double(), w_hh.double())
+    with torch.no_grad():
+        out = ops.lstm_layer(x.to(cuda_device), w_ih.to(cuda_device), w_hh.to(cuda_device))
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-5
+
+
+def test_lstm_unsupported_hidden_size(cuda_device):
+    x, w_ih, w_hh, _ = _lstm_case(2, 3, 6, 48, seed=5)
+    with pytest.raises(_lib.OpnError, match="unsupported"):
+        ops.lstm_layer(x.to(cuda_device), w_ih.to(cuda_device), w_hh.to(cuda_device))
+
+
+# ---- who-to-track ---------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,H1", [(1, 1, 32), (3, 11, 256), (5, 300, 64)])
+def test_who_to_track(cuda_device, B, T, H1):
+    from objectpermanence_b200.synthetic import make_batch
+    boxes = torch.from_numpy(make_batch(B, T, 6, seed=B + T)[0])
+    hs1, wp = _rand((B, T, H1), 31), _rand((15, H1), 32, 2.0 / math.sqrt(H1))
+    dfb, dlog = _rand((B, T, 6), 33), _rand((B, 15, T), 34)
+    hr, wr = hs1.double().requires_grad_(True), wp.double().requires_grad_(True)
+    fb_ref, logits_ref = oracle.who_to_track(boxes.double(), hr, wr)
+    logits_ref = logits_ref.permute(0, 2, 1).contiguous()
+    (fb_ref * dfb.double()).sum().add((logits_ref * dlog.double()).sum()).backward()
+
+    hg, wg = hs1.to(cuda_device).requires_grad_(True), wp.to(cuda_device).requires_grad_(True)
+    fb, logits = ops.who_to_track(boxes.to(cuda_device), hg, wg)
+    assert logits.shape == (B, 15, T)
+    assert (fb.detach().cpu().double() - fb_ref.detach()).abs().max().item() <= 1e-5
+    assert (logits.detach().cpu().double() - logits_ref.detach()).abs().max().item() <= 1e-5
+    ((fb * dfb.to(cuda_device)).sum() + (logits * dlog.to(cuda_device)).sum()).backward()
+    assert (hg.grad.cpu().double() - hr.grad).abs().max().item() <= 1e-5
+    assert (wg.grad.cpu().double() - wr.grad).abs().max().item() <= 2e-4
+
+
+# ---- encoder helpers ------------------------------------------------------------------------
+def test_add_layer_norm(cuda_device):
+    rows, D = 77, 256
+    x, r, w, b, dy = _rand((rows, D), 41), _rand((rows, D), 42), 1 + _rand((D,), 43, 0.1), _rand((D,), 44, 0.1), _rand(
+        (rows, D), 45)
+    xr, rr, wr, br = [t.double().requires_grad_(True) for t in (x, r, w, b)]
+    ref = oracle.layer_norm(xr + rr, wr, br)
+    ref.backward(dy.double())
+    xg, rg, wg, bg = [t.to(cuda_device).requires_grad_(True) for t in (x, r, w, b)]
+    out = ops.add_layer_norm(xg, rg, wg, bg)
+    out.backward(dy.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
+    for got, want in ((xg.grad, xr.grad), (rg.grad, rr.grad), (wg.grad, wr.grad), (bg.grad, br.grad)):
+        assert (got.cpu().double() - want).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("S,D,nhead", [(48, 32, 2), (300, 256, 2), (1000, 64, 4)])
+def test_self_attention(cuda_device, S, D, nhead):
+    qkv, dctx = _rand((S, 3 * D), 51), _rand((S, D), 52)
+    qr = qkv.double().requires_grad_(True)
+    d = D // nhead
+    q, k, v = [z.reshape(S, nhead, d).permute(1, 0, 2) for z in (qr[:, :D], qr[:, D:2 * D], qr[:, 2 * D:])]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1) @ v).permute(1, 0, 2).reshape(S, D)
+    ref.backward(dctx.double())
+    qg = qkv.to(cuda_device).requires_grad_(True)
+    out = ops.self_attention(qg, nhead)
+    out.backward(dctx.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
+    assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4
+
+
+def test_linear_bias_relu(cuda_device):
+    x, w, b, dy = _rand((4, 9, 20), 61), _rand((33, 20), 62), _rand((33,), 63), _rand((4, 9, 33), 64)
+    xr, wr, br = [t.double().requires_grad_(True) for t in (x, w, b)]
+    ref = torch.relu(xr @ wr.t() + br)
+    ref.backward(dy.double())
+    xg, wg, bg = [t.to(cuda_device).requires_grad_(True) for t in (x, w, b)]
+    out = ops.linear(xg, wg, bg, relu=True)
+    out.backward(dy.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
+    for got, want in ((xg.grad, xr.grad), (wg.grad, wr.grad), (bg.grad, br.grad)):
+        assert (got.cpu().double() - want).abs().max().item() <= 1e-4
+
+
+# ---- training loss --------------------------------------------------------------------------
+@pytest.mark.parametrize("no_labels", [False, True])
+def test_training_loss(cuda_device, no_labels):
+    B, T = 5, 37
+    y, labels = _rand((B, T, 4), 71, 0.5) + 0.5, _rand((B, T, 4), 72, 0.5) + 0.5
+    y[0, 3] = labels[0, 3]           # exact zeros: sign(0) = 0
+    y[1, 6] = y[1, 5]                # zero-length consistency step: sub-gradient 0
+    mask = (_rand((B, T, 1), 73) > 0).expand(B, T, 4).contiguous()
+    yr = y.double().requires_grad_(True)
+    ref = oracle.training_loss(yr, labels.double(), mask.double(), no_labels)
+    ref.backward()
+    yg = y.to(cuda_device).requires_grad_(True)
+    out = ops.training_loss(yg, labels.to(cuda_device), mask.to(cuda_device), no_labels)
+    out[0].backward()
+    assert abs(out[0].item() - ref.item()) <= 1e-6
+    assert (yg.grad.cpu().double() - yr.grad).abs().max().item() <= 1e-7
