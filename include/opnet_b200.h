@@ -71,7 +71,8 @@ OPN_API int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K,
  *   and their autograd backward (baselines/training_main.py:216).
  *
  * workspace: opn_lstm_workspace_bytes(B,T,H) bytes, owned by the caller, must stay alive
- *   until the stream has drained; contents are scratch (step counters, transposed W_hh).
+ *   until the stream has drained; contents are scratch (status word, the two exchange rings,
+ *   transposed W_hh).
  */
 OPN_API int64_t opn_lstm_workspace_bytes(int64_t B, int64_t T, int64_t H);
 

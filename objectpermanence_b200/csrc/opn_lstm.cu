@@ -7,21 +7,28 @@
 //     (forward: their 32 gate rows of W_hh; backward: their 8 columns of W_hh, i.e. 8 rows
 //     of W_hh^T) for one *batch group* of 8 videos.  The CTA's weight slice lives in
 //     registers for the whole sequence (8 rows x KPT values per thread, KPT = H/32).
-//   * Per step every CTA needs the full recurrent vector of its batch group
-//     (forward: h_{t-1} [8,H]; backward: dgates_t [8,4H]).  It is fetched from L2 into
-//     shared memory with TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) in up to four
-//     chunks, each completing its own mbarrier so the FFMA loop starts on chunk 0 while
-//     the rest is still in flight.
-//   * Cross-CTA ordering is a per-(batch group, step) arrival counter in global memory:
-//     producers red.release.gpu after storing their slice, the consumer's elected thread
-//     ld.acquire.gpu-polls it.  Batch groups are independent chains; two CTAs are resident
-//     per SM so one chain's wait overlaps another chain's FFMA work.
-//   * The [8 rows x 8 videos] partial sums of the thread tile are reduced across the
-//     K-split with a 62-shuffle transposing butterfly (no shared memory in the forward).
+//   * Per step every CTA needs the full recurrent vector of its batch group (forward:
+//     h_{t-1} [8,H]; backward: dgates_t [8,4H]).  It is exchanged through a 2-slot ring in
+//     global memory (L2 resident) with a *ready bit carried in the data*: the producer
+//     replaces the mantissa LSB of every exchanged fp32 word by the step parity and stores it
+//     with st.relaxed.gpu; consumers ld.relaxed.gpu the words they need and retry until every
+//     LSB shows the expected parity.  32-bit accesses are single-copy atomic, so a word is
+//     either stale (old parity) or complete: no fence, no atomic, no inter-CTA barrier is on
+//     the per-step critical path (the first version of this kernel used arrival counters +
+//     red.release / ld.acquire + TMA bulk copies and measured 3.5 us per step at H=256 where
+//     the FFMA work is 0.13 us; see profiles/r01_lstm_handoff.md).  The perturbation of the
+//     recurrent operand is <= 1 ulp (6e-8 relative); the tensors handed to the rest of the
+//     graph (hs, gates, cells, dgates) are stored exactly, off the critical path.
+//   * Batch groups are independent chains; two CTAs are resident per SM so one chain's
+//     exchange latency overlaps another chain's FFMA work.
+//   * The [8 rows x 8 videos] partial sums of the thread tile are reduced across the K-split
+//     with a 62-shuffle transposing butterfly.
 //   * sigmoid/tanh, the cell update and the stash writes are fused into the step.
 //
 // Every spin wait has a clock64() time-out: on expiry the kernel records a status word and
 // all CTAs leave the time loop (no hang, no trap).
+#include <stdlib.h>
+
 #include "opn_common.cuh"
 
 namespace opn {
@@ -34,7 +41,6 @@ constexpr int kUnits = 8;   // hidden units per CTA
 constexpr long long kTimeoutCycles = 3000000000LL;  // ~1.5 s at 2 GHz
 
 constexpr uint32_t kStatusPollTimeout = 1;
-constexpr uint32_t kStatusMbarTimeout = 2;
 
 struct FwdParams {
     const float* xproj;   // [B,T,4H]
@@ -42,11 +48,12 @@ struct FwdParams {
     float* hs;            // [B,T,H]
     float* gates;         // [B,T,4H] or null
     float* cells;         // [B,T,H] or null
-    unsigned int* counters;  // [n_groups_total][T]
-    unsigned int* status;    // 4 words
+    uint32_t* ring;       // [n_groups_total][2][8][H]   flagged copies of h_t
+    unsigned int* status; // 4 words
     int B, T;
     int group_offset;  // first batch group handled by this launch
     int n_slices;      // H / 8
+    int flags;         // debug knobs (OPN_LSTM_* environment): bit1 fence after publish, bit2 progress marks
 };
 
 struct BwdParams {
@@ -55,18 +62,93 @@ struct BwdParams {
     const float* cells;   // [B,T,H]
     const float* dh_out;  // [B,T,H]
     float* dgates;        // [B,T,4H]
-    unsigned int* counters;
+    uint32_t* ring;       // [n_groups_total][2][8][4H]  flagged copies of dgates_t
     unsigned int* status;
     int B, T;
     int group_offset;
     int n_slices;
+    int flags;
 };
 
-// k index of the e-th weight held by K-split `ks` (NS splits in total)
-template <int KPT, int NS>
-__device__ __forceinline__ int k_index(int ks, int e) {
-    if (KPT >= 4) return 4 * ks + (4 * NS) * (e >> 2) + (e & 3);
-    return ks + NS * e;
+// parity carried by the words of step t: slot t&1 is rewritten every 2 steps, so the bit
+// alternates per rewrite; the first write (t = 0, 1) carries 1 to differ from the zeroed ring.
+__device__ __forceinline__ uint32_t step_parity(int t) { return ((uint32_t)(t >> 1) & 1u) ^ 1u; }
+
+__device__ __forceinline__ void st_flagged(uint32_t* p, float v, uint32_t parity) {
+    const uint32_t bits = (__float_as_uint(v) & ~1u) | parity;
+    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(bits) : "memory");
+}
+__device__ __forceinline__ uint4 ld_flagged4(const uint32_t* p) {
+    uint4 v;
+    // ld.volatile streams at ~80 B/clk/SM from L2, ld.relaxed.gpu / ld.global.cg at ~40 and ld.acquire.gpu at ~3
+    // (measured with tools/load_flavors.cu, profiles/r01_lstm_handoff.md); every 32-bit element is still a
+    // single-copy-atomic access that is always served by L2.
+    asm volatile("ld.volatile.global.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_flagged1(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool ready4(const uint4& v, uint32_t parity) {
+    return ((((v.x ^ parity) | (v.y ^ parity) | (v.z ^ parity) | (v.w ^ parity)) & 1u) == 0u);
+}
+
+// Time-out bookkeeping of the polling loops: called every 64 unsuccessful sweeps.  Returns true
+// when the caller must give up (another CTA reported a failure, or this wait has expired).
+__device__ __noinline__ bool poll_expired(long long t0, unsigned int* status, int t) {
+    if (ld_relaxed(status) != 0) return true;
+    if (clock64() - t0 > kTimeoutCycles) {
+        if (atomicCAS(status, 0u, kStatusPollTimeout) == 0u) {
+            status[1] = (unsigned int)t;
+            status[2] = blockIdx.x;
+            status[3] = threadIdx.x;
+        }
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint4 ld_word(const uint4*, const uint32_t* p) { return ld_flagged4(p); }
+__device__ __forceinline__ uint32_t ld_word(const uint32_t*, const uint32_t* p) { return ld_flagged1(p); }
+__device__ __forceinline__ bool word_ready(const uint4& v, uint32_t parity) { return ready4(v, parity); }
+__device__ __forceinline__ bool word_ready(const uint32_t& v, uint32_t parity) { return (v & 1u) == parity; }
+
+// Fetch N flagged words (uint4 or uint32_t) whose addresses / validity are given by functors.
+// Every load of a sweep is issued back to back (one L2 round trip when the data is already there);
+// stale words are re-fetched in further sweeps.  (A variant that spun on a single canary word per
+// thread and fetched the rest afterwards was measured slower on B200 -- 10.0 vs 3.8 us/step for the
+// H=256 backward recurrence -- and was dropped; see profiles/r01_lstm_handoff.md.)
+// Returns false on time-out / abort.
+template <int N, typename Word, typename AddrFn, typename ValidFn>
+__device__ __forceinline__ bool gather_flagged(Word (&v)[N], AddrFn addr, ValidFn valid, uint32_t par,
+                                               unsigned int* status, int t) {
+    bool pending = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (valid(i)) v[i] = ld_word((const Word*)nullptr, addr(i));
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (valid(i) && !word_ready(v[i], par)) pending = true;
+    if (!pending) return true;
+
+    const long long t0 = clock64();
+    unsigned int sweeps = 0;
+    for (;;) {
+        pending = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (valid(i) && !word_ready(v[i], par)) v[i] = ld_word((const Word*)nullptr, addr(i));
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (valid(i) && !word_ready(v[i], par)) pending = true;
+        if (!pending) return true;
+        if ((++sweeps & 63u) == 0 && poll_expired(t0, status, t)) return false;
+    }
 }
 
 template <int KPT, int NS>
@@ -86,60 +168,19 @@ __device__ __forceinline__ void load_weight_row(float (&w)[KPT], const float* __
     }
 }
 
-// Wait for an mbarrier phase with a time-out.  Returns false on time-out / observed abort.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* status) {
-    if (mbar_try_wait(bar, parity)) return true;
-    long long t0 = clock64();
-    unsigned int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0) {
-            if (ld_relaxed(status) != 0) return false;
-            if (clock64() - t0 > kTimeoutCycles) {
-                atomicCAS(status, 0u, kStatusMbarTimeout);
-                return false;
-            }
-        }
-    }
-    return true;
-}
-
-// Elected-thread wait until *counter >= target.
-__device__ __forceinline__ bool poll_counter(const unsigned int* counter, unsigned int target, unsigned int* status,
-                                             int t) {
-    if (ld_acquire(counter) >= target) return true;
-    long long t0 = clock64();
-    unsigned int spins = 0;
-    while (ld_acquire(counter) < target) {
-        if ((++spins & 63u) == 0) {
-            if (ld_relaxed(status) != 0) return false;
-            if (clock64() - t0 > kTimeoutCycles) {
-                if (atomicCAS(status, 0u, kStatusPollTimeout) == 0u) {
-                    status[1] = (unsigned int)t;
-                    status[2] = blockIdx.x;
-                    status[3] = *counter;
-                }
-                return false;
-            }
-        }
-    }
-    return true;
-}
-
-// acc[rr*8 + b] += sum_e w[rr][e] * v_s[b][k_index(ks, e)]  for the thread's K-split.
-// v_s is the shared-memory copy of the recurrent vector, [8][K]; chunk c (K/NCH values per
-// row) is valid once bars[c] has completed the phase `parity`.
-template <int KPT, int NS>
-__device__ __forceinline__ bool matvec_tile(const float (&w)[kUnits][KPT], const float* v_s, int ks, uint64_t* bars,
-                                            uint32_t parity, unsigned int* status, float (&acc)[64]) {
-    constexpr int K = NS * KPT;
-    bool ok = true;
+// acc[rr*8 + b] += sum_e w[rr][e] * v(b, e) where, for KPT >= 4, the thread's operand vector
+// (b, j) is the float4 at v_s[(j*8 + b) * stride_vec + lane_vec]; for KPT < 4 the scalar (b, e)
+// is at v_s[(e*8 + b) * stride_vec + lane_vec].
+template <int KPT>
+__device__ __forceinline__ void matvec_tile(const float (&w)[kUnits][KPT], const float* v_s, int stride_vec,
+                                            int lane_vec, float (&acc)[64]) {
     if (KPT >= 4) {
+        const float4* v4 = reinterpret_cast<const float4*>(v_s);
 #pragma unroll
         for (int j = 0; j < KPT / 4; ++j) {
-            ok = mbar_wait(&bars[j], parity, status) && ok;
 #pragma unroll
             for (int b = 0; b < kGroup; ++b) {
-                const float4 hv = *reinterpret_cast<const float4*>(v_s + b * K + 4 * ks + (4 * NS) * j);
+                const float4 hv = v4[(j * 8 + b) * stride_vec + lane_vec];
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     float a = acc[rr * 8 + b];
@@ -152,18 +193,16 @@ __device__ __forceinline__ bool matvec_tile(const float (&w)[kUnits][KPT], const
             }
         }
     } else {
-        ok = mbar_wait(&bars[0], parity, status);
 #pragma unroll
         for (int e = 0; e < KPT; ++e) {
 #pragma unroll
             for (int b = 0; b < kGroup; ++b) {
-                const float hv = v_s[b * K + ks + NS * e];
+                const float hv = v_s[(e * 8 + b) * stride_vec + lane_vec];
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) acc[rr * 8 + b] = fmaf(w[rr][e], hv, acc[rr * 8 + b]);
             }
         }
     }
-    return ok;
 }
 
 // One stage of the transposing butterfly: the N live values (compact index) are halved; bit
@@ -193,31 +232,31 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[64], int lane) 
 // ------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------
-template <int KPT>
-__global__ void __launch_bounds__(kThreads, 2) lstm_fwd_kernel(const FwdParams p) {
+// Shared-memory operand layout (both kernels): "vector slot" (j, b) of K-split ks lives at
+// float4 index (j*8 + b) * NS + ks, so a warp's LDS.128 touches 32 consecutive 16-byte words.
+// RG = row groups per CTA (128*RG threads, 8*RG hidden units).  RG = 2 is used at H = 512 so that a
+// batch of 32 videos is exactly one CTA per SM: two 128-thread CTAs per SM were measured to serialise
+// (5.2 us/step against 3.0 us/step with one), because they share the SM's L2 request path while polling.
+template <int KPT, int RG>
+__global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kernel(const FwdParams p) {
     constexpr int H = 32 * KPT;
-    constexpr int NCH = (KPT >= 4) ? KPT / 4 : 1;
-    constexpr int CH = H / NCH;  // floats per chunk per video row
+    constexpr int NT = kThreads * RG;
+    constexpr int VPR = (KPT >= 4) ? H / 4 : H;        // exchange words per video row (vectors or scalars)
+    constexpr int NV = (8 * VPR + NT - 1) / NT;        // per-thread loads per step
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* h_s = reinterpret_cast<float*>(smem_raw);  // [8][H]
-    __shared__ __align__(8) uint64_t bars[4];
+    float* h_s = reinterpret_cast<float*>(smem_raw);  // [2][8*H]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slice = blockIdx.x % p.n_slices;
     const int group = p.group_offset + blockIdx.x / p.n_slices;
-    const int u0 = slice * kUnits;
+    const int u0 = slice * (kUnits * RG);
     const int b0 = group * kGroup;
     const int T = p.T;
     const int nvalid = min(kGroup, p.B - b0);
-    unsigned int* cnt = p.counters + (size_t)group * T;
+    uint32_t* ring = p.ring + (size_t)group * (2 * kGroup * H);
 
-    for (int i = tid; i < kGroup * H; i += kThreads) h_s[i] = 0.0f;
-    if (tid == 0) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) mbar_init(&bars[c], 1);
-        mbar_fence_init();
-    }
+    for (int i = tid; i < 2 * kGroup * H; i += NT) h_s[i] = 0.0f;
 
     // this warp's 8 gate rows: rr = uu*4 + gate, unit = u0 + 2*warp + uu
     float w[8][KPT];
@@ -226,7 +265,6 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_fwd_kernel(const FwdParams p
         const int row = (rr & 3) * H + u0 + 2 * warp + (rr >> 2);
         load_weight_row<KPT, 32>(w[rr], p.w_hh + (size_t)row * H, lane);
     }
-    fence_proxy_async_smem();  // zero-fill of h_s (generic proxy) before any TMA write to it
     __syncthreads();
 
     // after the butterfly this lane owns gates (2*gh, 2*gh+1) of cell (unit u, video bb)
@@ -238,7 +276,6 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_fwd_kernel(const FwdParams p
     const float* xp_ptr = p.xproj + row0 * (4 * H) + (size_t)(2 * gh) * H + u;
 
     float c_state = 0.0f;
-    uint32_t parity = 0;
     int my_abort = 0;
     float xp0 = 0.f, xp1 = 0.f;
     if (valid) {
@@ -252,33 +289,44 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_fwd_kernel(const FwdParams p
         for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
 
         if (t > 0) {
-            if (warp == 0) {
-                int ok = 1;
-                if (lane == 0) ok = poll_counter(&cnt[t - 1], (unsigned int)p.n_slices, p.status, t) ? 1 : 0;
-                ok = __shfl_sync(0xffffffffu, ok, 0);
-                if (ok) {
-                    fence_proxy_async_global();
-                    if (lane == 0) {
-#pragma unroll
-                        for (int c = 0; c < NCH; ++c) mbar_arrive_expect_tx(&bars[c], (uint32_t)(nvalid * CH * 4));
-                    }
-                    __syncwarp();
-                    for (int piece = lane; piece < kGroup * NCH; piece += 32) {
-                        const int b = piece / NCH, c = piece % NCH;
-                        if (b < nvalid)
-                            bulk_g2s(h_s + b * H + c * CH, p.hs + ((size_t)(b0 + b) * T + (t - 1)) * H + c * CH,
-                                     (uint32_t)(CH * 4), &bars[c]);
-                    }
-                } else {
+            // ---- gather h_{t-1} of this batch group: flagged words -> shared memory -------------
+            const uint32_t par = step_parity(t - 1);
+            const uint32_t* src = ring + (size_t)((t - 1) & 1) * (kGroup * H);
+            float* dst = h_s + ((t - 1) & 1) * (kGroup * H);
+            if (KPT >= 4) {
+                // vector idx = tid + 128*i: video b = idx / VPR, column col = idx % VPR (k = 4*col .. 4*col+3)
+                uint4 v[NV];
+                if (!gather_flagged(v, [&](int i) { return src + (size_t)(tid + NT * i) * 4; },
+                                    [&](int i) { return (tid + NT * i) / VPR < nvalid; }, par, p.status, t))
                     my_abort = 1;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int idx = tid + NT * i;
+                    const int b = idx / VPR, col = idx % VPR;
+                    // k = 4*ks + 128*j  ->  ks = col % 32, j = col / 32
+                    if (b < nvalid) reinterpret_cast<uint4*>(dst)[((col >> 5) * 8 + b) * 32 + (col & 31)] = v[i];
+                }
+            } else {
+                // scalar idx = tid + 128*i: video b = idx / H, k = idx % H = ks + 32*e
+                uint32_t v[NV];
+                if (!gather_flagged(v, [&](int i) { return src + tid + NT * i; },
+                                    [&](int i) { return (tid + NT * i) < 8 * VPR && (tid + NT * i) / VPR < nvalid; },
+                                    par, p.status, t))
+                    my_abort = 1;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int idx = tid + NT * i;
+                    const int b = idx / VPR, k = idx % VPR;
+                    if (idx < 8 * VPR && b < nvalid)
+                        reinterpret_cast<uint32_t*>(dst)[((k >> 5) * 8 + b) * 32 + (k & 31)] = v[i];
                 }
             }
-            if (!matvec_tile<KPT, 32>(w, h_s, lane, bars, parity, p.status, acc)) my_abort = 1;
-            parity ^= 1u;
+            if (__syncthreads_or(my_abort)) break;
+            matvec_tile<KPT>(w, dst, 32, lane, acc);
             warp_transpose_reduce(acc, lane);
         }
 
-        // fused pointwise: gate activations, cell update, stash
+        // fused pointwise: gate activations, cell update
         const float a0 = acc[0] + xp0;
         const float a1 = acc[1] + xp1;
         const float act0 = gh ? tanhf(a0) : sigmoid_acc(a0);  // gh=0: i      gh=1: g
@@ -292,6 +340,9 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_fwd_kernel(const FwdParams p
         c_state = fmaf(gf, c_state, gi * gg);
         const float hval = go * tanhf(c_state);
         if (valid) {
+            // critical path first: publish h_t to the other CTAs of this batch group
+            if (gh == 0 && t + 1 < T) st_flagged(ring + (size_t)(t & 1) * (kGroup * H) + bl * H + u, hval, step_parity(t));
+            if (p.flags & 2) __threadfence();
             const size_t row = row0 + t;
             if (gh == 0) {
                 p.hs[row * H + u] = hval;
@@ -311,53 +362,50 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_fwd_kernel(const FwdParams p
                 xp1 = __ldg(xp_ptr + (size_t)(t + 1) * (4 * H) + H);
             }
         }
-        fence_proxy_async_global();  // h_t stores (generic proxy) -> later TMA reads by other CTAs
-        const int abort = __syncthreads_or(my_abort);
-        if (abort) break;
-        if (tid == 0) red_release_add(&cnt[t], 1u);
     }
 }
 
 // ------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------
-template <int KPT>
-__global__ void __launch_bounds__(kThreads, 2) lstm_bwd_kernel(const BwdParams p) {
+// RG = row groups per CTA: a CTA has 128*RG threads and owns 8*RG hidden units.  The operand
+// dgates_t [8,4H] is fetched once per CTA, so RG = 2 halves the L2 traffic of the gather (used at
+// H = 512, where 2 x 64 KB per SM and step would make the kernel L2-bandwidth bound).
+template <int KPT, int RG>
+__global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kernel(const BwdParams p) {
     constexpr int H = 32 * KPT;
     constexpr int K = 4 * H;
-    constexpr int NCH = (KPT >= 4) ? KPT / 4 : 1;
-    constexpr int CH = K / NCH;
+    constexpr int NVT = (KPT >= 4) ? 2 * KPT : 8 * KPT;  // operand words per K-split per step
+    constexpr int NLD = NVT / RG;                        // words each thread fetches (the RG groups share them)
+    constexpr int ROUND = (NLD > 16) ? 16 : NLD;         // loads in flight per gather round
+    constexpr int UNITS = kUnits * RG;
+    constexpr int NT = kThreads * RG;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* da_s = reinterpret_cast<float*>(smem_raw);  // [8][4H]
-    __shared__ float red_s[4][64];
-    __shared__ __align__(8) uint64_t bars[4];
+    float* da_s = reinterpret_cast<float*>(smem_raw);  // operand staging [NVT][128] words
+    __shared__ float red_s[2][4 * RG][64];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = tid / kThreads, ks = tid % kThreads;
     const int slice = blockIdx.x % p.n_slices;
     const int group = p.group_offset + blockIdx.x / p.n_slices;
-    const int u0 = slice * kUnits;
+    const int u0 = slice * UNITS;
     const int b0 = group * kGroup;
     const int T = p.T;
     const int nvalid = min(kGroup, p.B - b0);
-    unsigned int* cnt = p.counters + (size_t)group * T;
+    uint32_t* ring = p.ring + (size_t)group * (2 * kGroup * K);
 
-    for (int i = tid; i < kGroup * K; i += kThreads) da_s[i] = 0.0f;
-    if (tid == 0) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) mbar_init(&bars[c], 1);
-        mbar_fence_init();
-    }
+    for (int i = tid; i < kGroup * K; i += NT) da_s[i] = 0.0f;  // rows of absent videos stay zero
 
-    // rows rr = the CTA's 8 units; this thread's K-split is tid (128 splits of 4H)
+    // rows rr = 8 units of this row group; the K-split of this thread is ks (128 splits of 4H)
     float w[8][KPT];
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr) load_weight_row<KPT, kThreads>(w[rr], p.w_t + (size_t)(u0 + rr) * K, tid);
-    fence_proxy_async_smem();
+    for (int rr = 0; rr < 8; ++rr)
+        load_weight_row<KPT, kThreads>(w[rr], p.w_t + (size_t)(u0 + 8 * rg + rr) * K, ks);
     __syncthreads();
 
-    // threads 0..63 own one cell (unit u0 + tid/8, video b0 + tid%8) of the recurrence state
-    const bool cell_thread = tid < 64;
+    // threads 0 .. 64*RG-1 own one cell (unit u0 + tid/8, video b0 + tid%8) of the recurrence state
+    const bool cell_thread = tid < 64 * RG;
     const int ul = tid >> 3, bl = tid & 7;
     const int u = u0 + ul;
     const int bb = b0 + bl;
@@ -379,10 +427,10 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_bwd_kernel(const BwdParams p
     };
     if (valid) load_stash(T - 1);
 
-    uint32_t parity = 0;
     int my_abort = 0;
 
     for (int t = T - 1; t >= 0; --t) {
+        const int s = T - 1 - t;  // step number of the reverse recurrence: ring slot s&1, parity of s
         if (valid) {
             const float dh = sdh + dh_rec;
             const float tc = tanhf(sc);
@@ -392,54 +440,84 @@ __global__ void __launch_bounds__(kThreads, 2) lstm_bwd_kernel(const BwdParams p
             const float d_g = dc * si;
             const float d_f = dc * scp;
             dc_carry = dc * sf;
+            const float ai = d_i * si * (1.0f - si);
+            const float af = d_f * sf * (1.0f - sf);
+            const float ag = d_g * (1.0f - sg * sg);
+            const float ao = d_o * so * (1.0f - so);
+            if (t > 0) {  // critical path first: publish dgates_t to the other CTAs of the group
+                uint32_t* r = ring + (size_t)(s & 1) * (kGroup * K) + bl * K + u;
+                const uint32_t par = step_parity(s);
+                st_flagged(r, ai, par);
+                st_flagged(r + H, af, par);
+                st_flagged(r + 2 * H, ag, par);
+                st_flagged(r + 3 * H, ao, par);
+                if (p.flags & 2) __threadfence();
+            }
             float* dg = p.dgates + (row0 + t) * (size_t)K + u;
-            dg[0] = d_i * si * (1.0f - si);
-            dg[H] = d_f * sf * (1.0f - sf);
-            dg[2 * H] = d_g * (1.0f - sg * sg);
-            dg[3 * H] = d_o * so * (1.0f - so);
+            dg[0] = ai;
+            dg[H] = af;
+            dg[2 * H] = ag;
+            dg[3 * H] = ao;
             if (t > 0) load_stash(t - 1);  // prefetch: lands while the matvec runs
         }
-        fence_proxy_async_global();
-        const int abort = __syncthreads_or(my_abort);
-        if (abort) break;
-        if (tid == 0) red_release_add(&cnt[t], 1u);
         if (t == 0) break;
+        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 1u;
 
-        if (warp == 0) {
-            int ok = 1;
-            if (lane == 0) ok = poll_counter(&cnt[t], (unsigned int)p.n_slices, p.status, t) ? 1 : 0;
-            ok = __shfl_sync(0xffffffffu, ok, 0);
-            if (ok) {
-                fence_proxy_async_global();
-                if (lane == 0) {
+        // ---- gather dgates_t of this batch group into the staging area --------------------------
+        // K-split ks consumes, for KPT >= 4, the vectors q = j*8 + b -> dgates_t[b][4*ks + 512*j .. +3]
+        // (for KPT < 4 the scalars q = e*8 + b -> dgates_t[b][ks + 128*e]); with RG = 2 the two row
+        // groups fetch alternate halves and share them through shared memory.
+        const uint32_t par = step_parity(s);
+        const uint32_t* src = ring + (size_t)(s & 1) * (kGroup * K);
+        if (KPT >= 4) {
+            uint4* stage = reinterpret_cast<uint4*>(da_s);
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) mbar_arrive_expect_tx(&bars[c], (uint32_t)(nvalid * CH * 4));
+            for (int r0 = 0; r0 < NLD; r0 += ROUND) {
+                uint4 v[ROUND];
+                // slot handled as i-th word of this round: q = (r0 + i) * RG + rg   (b = q & 7, j = q >> 3)
+                if (!gather_flagged(
+                        v, [&](int i) { const int q = (r0 + i) * RG + rg; return src + (size_t)(q & 7) * K + 4 * ks + 512 * (q >> 3); },
+                        [&](int i) { return (((r0 + i) * RG + rg) & 7) < nvalid; }, par, p.status, t))
+                    my_abort = 1;
+#pragma unroll
+                for (int i = 0; i < ROUND; ++i) {
+                    const int q = (r0 + i) * RG + rg;
+                    if ((q & 7) < nvalid) stage[q * kThreads + ks] = v[i];
                 }
-                __syncwarp();
-                for (int piece = lane; piece < kGroup * NCH; piece += 32) {
-                    const int b = piece / NCH, c = piece % NCH;
-                    if (b < nvalid)
-                        bulk_g2s(da_s + b * K + c * CH, p.dgates + ((size_t)(b0 + b) * T + t) * K + c * CH,
-                                 (uint32_t)(CH * 4), &bars[c]);
-                }
-            } else {
+            }
+        } else {
+            uint32_t* stage = reinterpret_cast<uint32_t*>(da_s);
+            uint32_t v[NLD];
+            if (!gather_flagged(
+                    v, [&](int i) { const int q = i * RG + rg; return src + (size_t)(q & 7) * K + ks + kThreads * (q >> 3); },
+                    [&](int i) { return ((i * RG + rg) & 7) < nvalid; }, par, p.status, t))
                 my_abort = 1;
+#pragma unroll
+            for (int i = 0; i < NLD; ++i) {
+                const int q = i * RG + rg;
+                if ((q & 7) < nvalid) stage[q * kThreads + ks] = v[i];
             }
         }
+        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 2u;
+        if (RG > 1) __syncthreads();  // operands are shared between the row groups
+        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 3u;
 
         float acc[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
-        if (!matvec_tile<KPT, kThreads>(w, da_s, tid, bars, parity, p.status, acc)) my_abort = 1;
-        parity ^= 1u;
+        matvec_tile<KPT>(w, da_s, kThreads, ks, acc);
         warp_transpose_reduce(acc, lane);
         {
             const int a_lo = (((lane >> 4) & 1) << 5) | ((lane & 1) << 4) | ((lane >> 1) & 7);
-            red_s[warp][a_lo] = acc[0];
-            red_s[warp][a_lo | 8] = acc[1];
+            red_s[s & 1][warp][a_lo] = acc[0];
+            red_s[s & 1][warp][a_lo | 8] = acc[1];
         }
-        __syncthreads();
-        if (cell_thread) dh_rec = red_s[0][tid] + red_s[1][tid] + red_s[2][tid] + red_s[3][tid];
+        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 4u;
+        if (__syncthreads_or(my_abort)) break;  // red_s is double buffered: one barrier per step
+        if (cell_thread) {
+            const int wb = (ul >> 3) * 4, a = (ul & 7) * 8 + bl;  // the 4 warps of this cell's row group
+            dh_rec = red_s[s & 1][wb][a] + red_s[s & 1][wb + 1][a] + red_s[s & 1][wb + 2][a] + red_s[s & 1][wb + 3][a];
+        }
     }
 }
 
@@ -459,42 +537,50 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 // ---- host side ----------------------------------------------------------------------
 struct WorkspaceLayout {
-    size_t status_off, fwd_cnt_off, bwd_cnt_off, wt_off, total;
+    size_t status_off, fwd_ring_off, bwd_ring_off, wt_off, total;
 };
 
 WorkspaceLayout layout(int64_t B, int64_t T, int64_t H) {
+    (void)T;
     const size_t groups = (size_t)((B + kGroup - 1) / kGroup);
     WorkspaceLayout l;
     l.status_off = 0;
-    l.fwd_cnt_off = 256;
-    const size_t cnt_bytes = ((groups * (size_t)T * sizeof(unsigned int)) + 255) / 256 * 256;
-    l.bwd_cnt_off = l.fwd_cnt_off + cnt_bytes;
-    l.wt_off = l.bwd_cnt_off + cnt_bytes;
+    l.fwd_ring_off = 4096;  // status block: 4 words + per-CTA progress marks (debug)
+    l.bwd_ring_off = l.fwd_ring_off + groups * 2 * kGroup * (size_t)H * sizeof(float);
+    l.wt_off = l.bwd_ring_off + groups * 2 * kGroup * 4 * (size_t)H * sizeof(float);
     l.total = l.wt_off + (size_t)H * 4 * H * sizeof(float);
     return l;
+}
+
+int debug_flags() {
+    int f = 0;
+    const char* e;
+    if ((e = getenv("OPN_LSTM_FENCE")) && e[0] == '1') f |= 2;
+    if ((e = getenv("OPN_LSTM_PROGRESS")) && e[0] == '1') f |= 4;
+    return f;
 }
 
 bool supported_hidden(int64_t H) { return H == 32 || H == 64 || H == 128 || H == 256 || H == 512; }
 
 template <typename Kernel>
-int max_coresident(Kernel kernel, size_t smem, int* out) {
+int max_coresident(Kernel kernel, int threads, size_t smem, int* out) {
     int dev = 0, sms = 0, per_sm = 0;
     OPN_CUDA(cudaGetDevice(&dev));
     OPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+    OPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     *out = sms * per_sm;
     return OPN_OK;
 }
 
-template <int KPT>
+template <int KPT, int RG>
 int launch_fwd(FwdParams p, int64_t B, cudaStream_t stream) {
     constexpr int H = 32 * KPT;
-    const size_t smem = (size_t)kGroup * H * sizeof(float);
+    const size_t smem = (size_t)2 * kGroup * H * sizeof(float);
     int cap = 0;
-    int rc = max_coresident(lstm_fwd_kernel<KPT>, smem, &cap);
+    int rc = max_coresident(lstm_fwd_kernel<KPT, RG>, kThreads * RG, smem, &cap);
     if (rc != OPN_OK) return rc;
-    const int n_slices = H / kUnits;
+    const int n_slices = H / (kUnits * RG);
     const int groups = (int)((B + kGroup - 1) / kGroup);
     const int per_launch = cap / n_slices;
     if (per_launch < 1) {
@@ -506,21 +592,24 @@ int launch_fwd(FwdParams p, int64_t B, cudaStream_t stream) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
         void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel<KPT>, dim3(n_slices * ng), dim3(kThreads),
-                                             args, smem, stream));
+        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel<KPT, RG>, dim3(n_slices * ng),
+                                             dim3(kThreads * RG), args, smem, stream));
         count_launch();
     }
     return OPN_OK;
 }
 
-template <int KPT>
+template <int KPT, int RG>
 int launch_bwd(BwdParams p, int64_t B, cudaStream_t stream) {
     constexpr int H = 32 * KPT;
     const size_t smem = (size_t)kGroup * 4 * H * sizeof(float);
-    int cap = 0;
-    int rc = max_coresident(lstm_bwd_kernel<KPT>, smem, &cap);
-    if (rc != OPN_OK) return rc;
-    const int n_slices = H / kUnits;
+    int dev = 0, sms = 0, per_sm = 0;
+    OPN_CUDA(cudaGetDevice(&dev));
+    OPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    OPN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<KPT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel<KPT, RG>, kThreads * RG, smem));
+    const int cap = sms * per_sm;
+    const int n_slices = H / (kUnits * RG);
     const int groups = (int)((B + kGroup - 1) / kGroup);
     const int per_launch = cap / n_slices;
     if (per_launch < 1) {
@@ -532,8 +621,8 @@ int launch_bwd(BwdParams p, int64_t B, cudaStream_t stream) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
         void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KPT>, dim3(n_slices * ng), dim3(kThreads),
-                                             args, smem, stream));
+        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KPT, RG>, dim3(n_slices * ng),
+                                             dim3(kThreads * RG), args, smem, stream));
         count_launch();
     }
     return OPN_OK;
@@ -563,25 +652,30 @@ extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj,
                   (long long)workspace_bytes, (long long)l.total);
     cudaStream_t s = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
-    OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, l.bwd_cnt_off - l.status_off, s));
+    OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, l.bwd_ring_off - l.status_off, s));  // status + forward ring
     FwdParams p;
     p.xproj = xproj;
     p.w_hh = w_hh;
     p.hs = hs;
     p.gates = gates;
     p.cells = cells;
-    p.counters = reinterpret_cast<unsigned int*>(ws + l.fwd_cnt_off);
+    p.ring = reinterpret_cast<uint32_t*>(ws + l.fwd_ring_off);
     p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
     p.B = (int)B;
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
+    p.flags = debug_flags();
     switch (H) {
-        case 32: return launch_fwd<1>(p, B, s);
-        case 64: return launch_fwd<2>(p, B, s);
-        case 128: return launch_fwd<4>(p, B, s);
-        case 256: return launch_fwd<8>(p, B, s);
-        default: return launch_fwd<16>(p, B, s);
+        case 32: return launch_fwd<1, 1>(p, B, s);
+        case 64: return launch_fwd<2, 1>(p, B, s);
+        case 128: return launch_fwd<4, 1>(p, B, s);
+        case 256: return launch_fwd<8, 1>(p, B, s);
+        default: {
+            const char* e = getenv("OPN_LSTM_FWD_RG");
+            if (e && e[0] == '1') return launch_fwd<16, 1>(p, B, s);
+            return launch_fwd<16, 2>(p, B, s);
+        }
     }
 }
 
@@ -598,8 +692,8 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     OPN_CHECK_ARG(workspace_bytes >= (int64_t)l.total, "lstm_bwd: workspace too small");
     cudaStream_t s = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
-    OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, 256, s));
-    OPN_CUDA(cudaMemsetAsync(ws + l.bwd_cnt_off, 0, l.wt_off - l.bwd_cnt_off, s));
+    OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, 4096, s));
+    OPN_CUDA(cudaMemsetAsync(ws + l.bwd_ring_off, 0, l.wt_off - l.bwd_ring_off, s));
     float* w_t = reinterpret_cast<float*>(ws + l.wt_off);
     {
         dim3 grid((unsigned)((H + 31) / 32), (unsigned)((4 * H + 31) / 32));
@@ -613,18 +707,23 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     p.cells = cells;
     p.dh_out = dh_out;
     p.dgates = dgates;
-    p.counters = reinterpret_cast<unsigned int*>(ws + l.bwd_cnt_off);
+    p.ring = reinterpret_cast<uint32_t*>(ws + l.bwd_ring_off);
     p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
     p.B = (int)B;
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
+    p.flags = debug_flags();
+    {
+        const char* e = getenv("OPN_LSTM_BWD_RG");
+        if (H == 512 && e && e[0] == '1') return launch_bwd<16, 1>(p, B, s);
+    }
     switch (H) {
-        case 32: return launch_bwd<1>(p, B, s);
-        case 64: return launch_bwd<2>(p, B, s);
-        case 128: return launch_bwd<4>(p, B, s);
-        case 256: return launch_bwd<8>(p, B, s);
-        default: return launch_bwd<16>(p, B, s);
+        case 32: return launch_bwd<1, 1>(p, B, s);
+        case 64: return launch_bwd<2, 1>(p, B, s);
+        case 128: return launch_bwd<4, 1>(p, B, s);
+        case 256: return launch_bwd<8, 1>(p, B, s);
+        default: return launch_bwd<16, 2>(p, B, s);
     }
 }
 
@@ -639,7 +738,7 @@ extern "C" int opn_lstm_status(const void* workspace, uint32_t* info) {
         info[2] = words[3];
     }
     if (words[0] != 0) {
-        set_error("persistent LSTM kernel timed out (code %u, step %u, cta %u, counter %u)", words[0], words[1],
+        set_error("persistent LSTM kernel timed out (code %u, step %u, cta %u, thread %u)", words[0], words[1],
                   words[2], words[3]);
         return OPN_ERR_TIMEOUT;
     }

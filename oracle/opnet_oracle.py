@@ -67,6 +67,8 @@ _FAMILY = {
     "non_linear_lstm": "non_linear_lstm", "non_linear_lstm_no_labels": "non_linear_lstm",
     "transformer_lstm": "transformer_lstm", "transformer_lstm_no_labels": "transformer_lstm",
     "opnet": "opnet", "opent_no_labels": "opnet",
+    "opnet_no_labels": "opnet",  # offered by the reference CLI (supported_models.py:12,30); its factory only
+                                  # matches the misspelling above, the B200 factory accepts both
     "opnet_lstm_mlp": "opnet_lstm_mlp", "opnet_lstm_mlp_no_labels": "opnet_lstm_mlp",
 }
 

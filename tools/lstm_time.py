@@ -1,0 +1,26 @@
+"""Time the persistent LSTM kernels alone (CUDA events) for a few shapes; prints us/step."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from objectpermanence_b200 import _lib
+from ctypes import c_uint32
+lib = _lib.load(); dev = torch.device("cuda:0")
+T = 300
+import itertools
+for B, H in itertools.product([int(x) for x in os.environ.get("BS", "32").split(",")], (256, 512)):
+    xp = torch.randn(B, T, 4 * H, device=dev) * 0.5
+    whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / (H ** 0.5)
+    hs = torch.empty(B, T, H, device=dev); gates = torch.empty(B, T, 4 * H, device=dev); cells = torch.empty(B, T, H, device=dev)
+    dh = torch.randn(B, T, H, device=dev) * 0.01; dg = torch.empty(B, T, 4 * H, device=dev)
+    ws = torch.empty(lib.opn_lstm_workspace_bytes(B, T, H), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    fwd = lambda: _lib.check(lib.opn_lstm_fwd(B, T, H, xp.data_ptr(), whh.data_ptr(), hs.data_ptr(), gates.data_ptr(), cells.data_ptr(), ws.data_ptr(), ws.numel(), s))
+    bwd = lambda: _lib.check(lib.opn_lstm_bwd(B, T, H, whh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dh.data_ptr(), dg.data_ptr(), ws.data_ptr(), ws.numel(), s))
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        fwd(); fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): fn()
+        e1.record(); torch.cuda.synchronize()
+        info = (c_uint32 * 3)(); rc = lib.opn_lstm_status(ws.data_ptr(), info)
+        print(f"B={B} H={H} {name}: {e0.elapsed_time(e1) / 3 * 1e3 / T:8.3f} us/step  status={rc} {list(info) if rc else ''}", flush=True)
