@@ -57,12 +57,12 @@ struct FwdParams {
 };
 
 struct BwdParams {
-    const float* w_t;     // [H,4H]  (W_hh transposed)
+    const float* w_hh;    // [4H,H]
     const float* gates;   // [B,T,4H]
     const float* cells;   // [B,T,H]
     const float* dh_out;  // [B,T,H]
     float* dgates;        // [B,T,4H]
-    uint32_t* ring;       // [n_groups_total][2][8][4H]  flagged copies of dgates_t
+    uint32_t* ring;       // [n_groups_total][2][H/U producers][8][H]  flagged partial products
     unsigned int* status;
     int B, T;
     int group_offset;
@@ -207,8 +207,8 @@ __device__ __forceinline__ void matvec_tile(const float (&w)[kUnits][KPT], const
 
 // One stage of the transposing butterfly: the N live values (compact index) are halved; bit
 // ABIT of the compact index is resolved by lane bit `mask`.
-template <int N, int ABIT>
-__device__ __forceinline__ void butterfly_stage(float (&v)[64], bool hi, int mask) {
+template <int N, int ABIT, int SZ>
+__device__ __forceinline__ void butterfly_stage(float (&v)[SZ], bool hi, int mask) {
 #pragma unroll
     for (int i = 0; i < N / 2; ++i) {
         const int lo = ((i >> ABIT) << (ABIT + 1)) | (i & ((1 << ABIT) - 1));
@@ -222,11 +222,21 @@ __device__ __forceinline__ void butterfly_stage(float (&v)[64], bool hi, int mas
 // Sum acc[64] over the 32 lanes of the warp.  On return lane l holds in v[0], v[1] the totals
 // of index  a = ((l>>4)&1)<<5 | (l&1)<<4 | j<<3 | ((l>>1)&7)   for j = 0, 1.
 __device__ __forceinline__ void warp_transpose_reduce(float (&v)[64], int lane) {
-    butterfly_stage<64, 5>(v, (lane & 16) != 0, 16);
-    butterfly_stage<32, 2>(v, (lane & 8) != 0, 8);
-    butterfly_stage<16, 1>(v, (lane & 4) != 0, 4);
-    butterfly_stage<8, 0>(v, (lane & 2) != 0, 2);
-    butterfly_stage<4, 1>(v, (lane & 1) != 0, 1);
+    butterfly_stage<64, 5, 64>(v, (lane & 16) != 0, 16);
+    butterfly_stage<32, 2, 64>(v, (lane & 8) != 0, 8);
+    butterfly_stage<16, 1, 64>(v, (lane & 4) != 0, 4);
+    butterfly_stage<8, 0, 64>(v, (lane & 2) != 0, 2);
+    butterfly_stage<4, 1, 64>(v, (lane & 1) != 0, 1);
+}
+
+// Sum v[16] over the 32 lanes.  On return v[0] of lane l is the total of index l >> 1 (both lanes of a pair
+// hold it).
+__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
+    butterfly_stage<16, 3, 16>(v, (lane & 16) != 0, 16);
+    butterfly_stage<8, 2, 16>(v, (lane & 8) != 0, 8);
+    butterfly_stage<4, 1, 16>(v, (lane & 4) != 0, 4);
+    butterfly_stage<2, 0, 16>(v, (lane & 2) != 0, 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // ------------------------------------------------------------------------------------
@@ -368,55 +378,87 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
 // ------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------
-// RG = row groups per CTA: a CTA has 128*RG threads and owns 8*RG hidden units.  The operand
-// dgates_t [8,4H] is fetched once per CTA, so RG = 2 halves the L2 traffic of the gather (used at
-// H = 512, where 2 x 64 KB per SM and step would make the kernel L2-bandwidth bound).
+// Reduce-scatter formulation.  The CTA keeps the same slice of W_hh as the forward CTA -- the 4*U gate rows
+// of its U = 8*RG hidden units, all H columns, in registers (thread tid owns columns KC*tid .. KC*tid+KC-1).
+// Per step t (descending):
+//   1. the lane pairs that own the U x 8 (unit, video) cells turn dh_t (upstream + recurrent) and the stash
+//      into d(pre-activation gates) for the CTA's own units, store them (exactly) to `dgates` and into
+//      shared memory [4U][8];
+//   2. every thread accumulates partial[b][k] = sum_{own rows r} da[b][r] * W_hh[r][k] for its columns and
+//      publishes the 8 x KC partial sums as flagged words into its producer region of the ring;
+//   3. the CTA gathers, for its own units only, the partials of all H/U producers of the batch group and
+//      sums them (in-thread adds + a short shuffle butterfly): dh_rec_{t-1}[unit, video] lands in the lane
+//      pair that owns that cell.  The ring is laid out per CONSUMER, [consumer][video][producer][unit], so
+//      this gather is one contiguous, fully coalesced block (4 uint4 per thread); with a per-producer
+//      layout every warp load touched 32 different lines and H=256 ran at 4.05 us/step.
+// Per CTA and step 8*H*4 bytes are written and read (16 KB at H=512) against 8*4H*4 bytes read by the
+// gather formulation of the first version (64 KB, 6.05 us/step); no transposed copy of W_hh is needed.
 template <int KPT, int RG>
 __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kernel(const BwdParams p) {
     constexpr int H = 32 * KPT;
-    constexpr int K = 4 * H;
-    constexpr int NVT = (KPT >= 4) ? 2 * KPT : 8 * KPT;  // operand words per K-split per step
-    constexpr int NLD = NVT / RG;                        // words each thread fetches (the RG groups share them)
-    constexpr int ROUND = (NLD > 16) ? 16 : NLD;         // loads in flight per gather round
-    constexpr int UNITS = kUnits * RG;
     constexpr int NT = kThreads * RG;
+    constexpr int U = kUnits * RG;            // hidden units of this CTA
+    constexpr int R = 4 * U;                  // its gate rows
+    constexpr int KC = (H >= NT) ? H / NT : 1;  // columns per active thread
+    constexpr int NACT = H / KC;              // threads that take part in the matvec
+    constexpr int NS = H / U;                 // producers (slices) per batch group, <= 32
+    constexpr int VPC = U / 4;                // uint4 per (producer, video) holding this CTA's units
+    static_assert(NS <= 32 && 8 * VPC == 4 * (NT / 32), "4 gather vectors per thread");
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* da_s = reinterpret_cast<float*>(smem_raw);  // operand staging [NVT][128] words
-    __shared__ float red_s[2][4 * RG][64];
+    __shared__ __align__(16) float da_s[2][R][8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rg = tid / kThreads, ks = tid % kThreads;
     const int slice = blockIdx.x % p.n_slices;
     const int group = p.group_offset + blockIdx.x / p.n_slices;
-    const int u0 = slice * UNITS;
+    const int u0 = slice * U;
     const int b0 = group * kGroup;
     const int T = p.T;
     const int nvalid = min(kGroup, p.B - b0);
-    uint32_t* ring = p.ring + (size_t)group * (2 * kGroup * K);
+    constexpr size_t kSlotWords = (size_t)NS * kGroup * H;
+    uint32_t* ring = p.ring + (size_t)group * (2 * kSlotWords);
 
-    for (int i = tid; i < kGroup * K; i += NT) da_s[i] = 0.0f;  // rows of absent videos stay zero
+    for (int i = tid; i < 2 * R * 8; i += NT) (&da_s[0][0][0])[i] = 0.0f;  // rows of absent videos stay zero
 
-    // rows rr = 8 units of this row group; the K-split of this thread is ks (128 splits of 4H)
-    float w[8][KPT];
+    // weights: local row r = gate*U + unit  ->  W_hh row gate*H + u0 + unit, columns KC*tid ..
+    float w[R][KC];
+    if (tid < NACT) {
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr)
-        load_weight_row<KPT, kThreads>(w[rr], p.w_t + (size_t)(u0 + 8 * rg + rr) * K, ks);
-    __syncthreads();
+        for (int r = 0; r < R; ++r) {
+            const float* row = p.w_hh + (size_t)((r / U) * H + u0 + (r % U)) * H + KC * tid;
+            if (KC == 2) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(row));
+                w[r][0] = v.x;
+                w[r][KC - 1] = v.y;
+            } else {
+                w[r][0] = __ldg(row);
+            }
+        }
+    }
 
-    // threads 0 .. 64*RG-1 own one cell (unit u0 + tid/8, video b0 + tid%8) of the recurrence state
-    const bool cell_thread = tid < 64 * RG;
-    const int ul = tid >> 3, bl = tid & 7;
+    // Cell ownership after the reduction of step 3 (see there):
+    //   RG = 1: warp w gathers videos 2w, 2w+1; lane l ends with video 2w + (l>>4), unit 4*(l&1) + ((l>>2)&3)
+    //   RG = 2: warp w gathers video w;         lane l ends with unit 4*(l&3) + ((l>>3)&3)
+    // two lanes hold every cell (they differ in lane bit 1 resp. 2): `half` splits the gate work between them.
+    int bl, ul, half;
+    if (RG == 1) {
+        bl = 2 * warp + (lane >> 4);
+        ul = 4 * (lane & 1) + ((lane >> 2) & 3);
+        half = (lane >> 1) & 1;
+    } else {
+        bl = warp;
+        ul = 4 * (lane & 3) + ((lane >> 3) & 3);
+        half = (lane >> 2) & 1;
+    }
     const int u = u0 + ul;
     const int bb = b0 + bl;
-    const bool valid = cell_thread && (bb < p.B);
+    const bool valid = bb < p.B;
     const size_t row0 = (size_t)(valid ? bb : 0) * T;
 
     float dc_carry = 0.0f, dh_rec = 0.0f;
     float si = 0.f, sf = 0.f, sg = 0.f, so = 0.f, sc = 0.f, scp = 0.f, sdh = 0.f;
     auto load_stash = [&](int t) {
         const size_t row = row0 + t;
-        const float* g = p.gates + row * (size_t)K + u;
+        const float* g = p.gates + row * (size_t)(4 * H) + u;
         si = __ldg(g);
         sf = __ldg(g + H);
         sg = __ldg(g + 2 * H);
@@ -426,11 +468,14 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
         sdh = __ldg(p.dh_out + row * H + u);
     };
     if (valid) load_stash(T - 1);
+    __syncthreads();
 
     int my_abort = 0;
 
     for (int t = T - 1; t >= 0; --t) {
         const int s = T - 1 - t;  // step number of the reverse recurrence: ring slot s&1, parity of s
+        const int buf = s & 1;
+        // ---- 1. cell backward for the CTA's own units ---------------------------------------------------
         if (valid) {
             const float dh = sdh + dh_rec;
             const float tc = tanhf(sc);
@@ -440,105 +485,120 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
             const float d_g = dc * si;
             const float d_f = dc * scp;
             dc_carry = dc * sf;
-            const float ai = d_i * si * (1.0f - si);
-            const float af = d_f * sf * (1.0f - sf);
-            const float ag = d_g * (1.0f - sg * sg);
-            const float ao = d_o * so * (1.0f - so);
-            if (t > 0) {  // critical path first: publish dgates_t to the other CTAs of the group
-                uint32_t* r = ring + (size_t)(s & 1) * (kGroup * K) + bl * K + u;
-                const uint32_t par = step_parity(s);
-                st_flagged(r, ai, par);
-                st_flagged(r + H, af, par);
-                st_flagged(r + 2 * H, ag, par);
-                st_flagged(r + 3 * H, ao, par);
-                if (p.flags & 2) __threadfence();
+            float* dg = p.dgates + (row0 + t) * (size_t)(4 * H) + u;
+            if (half == 0) {
+                const float ai = d_i * si * (1.0f - si);
+                const float af = d_f * sf * (1.0f - sf);
+                da_s[buf][ul][bl] = ai;
+                da_s[buf][U + ul][bl] = af;
+                dg[0] = ai;
+                dg[H] = af;
+            } else {
+                const float ag = d_g * (1.0f - sg * sg);
+                const float ao = d_o * so * (1.0f - so);
+                da_s[buf][2 * U + ul][bl] = ag;
+                da_s[buf][3 * U + ul][bl] = ao;
+                dg[2 * H] = ag;
+                dg[3 * H] = ao;
             }
-            float* dg = p.dgates + (row0 + t) * (size_t)K + u;
-            dg[0] = ai;
-            dg[H] = af;
-            dg[2 * H] = ag;
-            dg[3 * H] = ao;
-            if (t > 0) load_stash(t - 1);  // prefetch: lands while the matvec runs
+            if (t > 0) load_stash(t - 1);  // prefetch: lands while the matvec and the exchange run
         }
         if (t == 0) break;
-        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 1u;
+        if (__syncthreads_or(my_abort)) break;  // da_s[buf] complete (double buffered: one barrier per step)
 
-        // ---- gather dgates_t of this batch group into the staging area --------------------------
-        // K-split ks consumes, for KPT >= 4, the vectors q = j*8 + b -> dgates_t[b][4*ks + 512*j .. +3]
-        // (for KPT < 4 the scalars q = e*8 + b -> dgates_t[b][ks + 128*e]); with RG = 2 the two row
-        // groups fetch alternate halves and share them through shared memory.
+        // ---- 2. partial[b][k] over the own rows; publish ------------------------------------------------
         const uint32_t par = step_parity(s);
-        const uint32_t* src = ring + (size_t)(s & 1) * (kGroup * K);
-        if (KPT >= 4) {
-            uint4* stage = reinterpret_cast<uint4*>(da_s);
+        uint32_t* slot = ring + (size_t)buf * kSlotWords;
+        if (tid < NACT) {
+            float acc[8][KC];
 #pragma unroll
-            for (int r0 = 0; r0 < NLD; r0 += ROUND) {
-                uint4 v[ROUND];
-                // slot handled as i-th word of this round: q = (r0 + i) * RG + rg   (b = q & 7, j = q >> 3)
-                if (!gather_flagged(
-                        v, [&](int i) { const int q = (r0 + i) * RG + rg; return src + (size_t)(q & 7) * K + 4 * ks + 512 * (q >> 3); },
-                        [&](int i) { return (((r0 + i) * RG + rg) & 7) < nvalid; }, par, p.status, t))
-                    my_abort = 1;
+            for (int b = 0; b < 8; ++b)
 #pragma unroll
-                for (int i = 0; i < ROUND; ++i) {
-                    const int q = (r0 + i) * RG + rg;
-                    if ((q & 7) < nvalid) stage[q * kThreads + ks] = v[i];
+                for (int c = 0; c < KC; ++c) acc[b][c] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 d0 = *reinterpret_cast<const float4*>(&da_s[buf][r][0]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&da_s[buf][r][4]);
+                const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int b = 0; b < 8; ++b)
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) acc[b][c] = fmaf(d[b], w[r][c], acc[b][c]);
+            }
+            // column k = KC*tid belongs to consumer k / U, unit k % U: word [consumer][b][producer = slice][unit]
+            const int k0 = KC * tid;
+            uint32_t* out = slot + ((size_t)(k0 / U) * kGroup * NS + slice) * U + (k0 % U);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < nvalid) {
+                    uint32_t* dst = out + (size_t)b * NS * U;
+                    if (KC == 2) {
+                        const uint32_t x = (__float_as_uint(acc[b][0]) & ~1u) | par;
+                        const uint32_t y = (__float_as_uint(acc[b][KC - 1]) & ~1u) | par;
+                        asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(x), "r"(y) : "memory");
+                    } else {
+                        st_flagged(dst, acc[b][0], par);
+                    }
                 }
             }
-        } else {
-            uint32_t* stage = reinterpret_cast<uint32_t*>(da_s);
-            uint32_t v[NLD];
+        }
+
+        // ---- 3. reduce-scatter: sum the producers' partials for the own units ---------------------------
+        {
+            // this CTA's block of the slot: [b][producer][U] words = per video NS*VPC uint4, contiguous
+            const uint32_t* src = slot + (size_t)slice * kGroup * NS * U;
+            uint4 v[4];
+            // load i of lane l:  RG=1: video 2w + (i>>1), vector (i&1)*32 + l  ->  producer vec/2, unit quad l&1
+            //                    RG=2: video w,            vector i*32 + l      ->  producer vec/4, unit quad l&3
+            auto vec_b = [&](int i) { return RG == 1 ? 2 * warp + (i >> 1) : warp; };
+            auto vec_id = [&](int i) { return RG == 1 ? (i & 1) * 32 + lane : i * 32 + lane; };
             if (!gather_flagged(
-                    v, [&](int i) { const int q = i * RG + rg; return src + (size_t)(q & 7) * K + ks + kThreads * (q >> 3); },
-                    [&](int i) { return ((i * RG + rg) & 7) < nvalid; }, par, p.status, t))
+                    v, [&](int i) { return src + ((size_t)vec_b(i) * NS * VPC + vec_id(i)) * 4; },
+                    [&](int i) { return vec_id(i) < NS * VPC && vec_b(i) < nvalid; }, par, p.status, t))
                 my_abort = 1;
+            float f[4][4];
 #pragma unroll
-            for (int i = 0; i < NLD; ++i) {
-                const int q = i * RG + rg;
-                if ((q & 7) < nvalid) stage[q * kThreads + ks] = v[i];
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = vec_id(i) < NS * VPC && vec_b(i) < nvalid;
+                f[i][0] = ok ? __uint_as_float(v[i].x) : 0.0f;
+                f[i][1] = ok ? __uint_as_float(v[i].y) : 0.0f;
+                f[i][2] = ok ? __uint_as_float(v[i].z) : 0.0f;
+                f[i][3] = ok ? __uint_as_float(v[i].w) : 0.0f;
+            }
+            if (RG == 1) {
+                // 8 values (video bit, j): in-thread sum over the two producer halves, then over lane bits 4,3,2
+                // with a butterfly (value index bit 2 = video, bits 1..0 = j) and over lane bit 1 with a plain add
+                float r8[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    r8[j] = f[0][j] + f[1][j];
+                    r8[4 + j] = f[2][j] + f[3][j];
+                }
+                butterfly_stage<8, 2, 8>(r8, (lane & 16) != 0, 16);
+                butterfly_stage<4, 1, 8>(r8, (lane & 8) != 0, 8);
+                butterfly_stage<2, 0, 8>(r8, (lane & 4) != 0, 4);
+                dh_rec = r8[0] + __shfl_xor_sync(0xffffffffu, r8[0], 2);
+            } else {
+                // 4 values (j): in-thread sum over the four producer octets, butterfly over lane bits 4,3,
+                // plain add over lane bit 2
+                float r4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r4[j] = (f[0][j] + f[1][j]) + (f[2][j] + f[3][j]);
+                butterfly_stage<4, 1, 4>(r4, (lane & 16) != 0, 16);
+                butterfly_stage<2, 0, 4>(r4, (lane & 8) != 0, 8);
+                dh_rec = r4[0] + __shfl_xor_sync(0xffffffffu, r4[0], 4);
             }
         }
-        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 2u;
-        if (RG > 1) __syncthreads();  // operands are shared between the row groups
-        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 3u;
-
-        float acc[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
-        matvec_tile<KPT>(w, da_s, kThreads, ks, acc);
-        warp_transpose_reduce(acc, lane);
-        {
-            const int a_lo = (((lane >> 4) & 1) << 5) | ((lane & 1) << 4) | ((lane >> 1) & 7);
-            red_s[s & 1][warp][a_lo] = acc[0];
-            red_s[s & 1][warp][a_lo | 8] = acc[1];
-        }
-        if ((p.flags & 4) && (tid & 127) == 0 && blockIdx.x < 250) p.status[16 + 2 * blockIdx.x + rg] = (unsigned)(s << 4) | 4u;
-        if (__syncthreads_or(my_abort)) break;  // red_s is double buffered: one barrier per step
-        if (cell_thread) {
-            const int wb = (ul >> 3) * 4, a = (ul & 7) * 8 + bl;  // the 4 warps of this cell's row group
-            dh_rec = red_s[s & 1][wb][a] + red_s[s & 1][wb + 1][a] + red_s[s & 1][wb + 2][a] + red_s[s & 1][wb + 3][a];
-        }
-    }
-}
-
-__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-    __shared__ float tile[32][33];
-    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int r = by + j, c = bx + threadIdx.x;
-        if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
-    }
-    __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int c = bx + j, r = by + threadIdx.x;
-        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
     }
 }
 
 // ---- host side ----------------------------------------------------------------------
 struct WorkspaceLayout {
-    size_t status_off, fwd_ring_off, bwd_ring_off, wt_off, total;
+    size_t status_off, fwd_ring_off, bwd_ring_off, total;
 };
+
+// units per CTA (8 or 16): 16 at H = 512 so that B = 32 is one CTA per SM
+int units_per_cta(int64_t H) { return H == 512 ? 2 * kUnits : kUnits; }
 
 WorkspaceLayout layout(int64_t B, int64_t T, int64_t H) {
     (void)T;
@@ -547,8 +607,8 @@ WorkspaceLayout layout(int64_t B, int64_t T, int64_t H) {
     l.status_off = 0;
     l.fwd_ring_off = 4096;  // status block: 4 words + per-CTA progress marks (debug)
     l.bwd_ring_off = l.fwd_ring_off + groups * 2 * kGroup * (size_t)H * sizeof(float);
-    l.wt_off = l.bwd_ring_off + groups * 2 * kGroup * 4 * (size_t)H * sizeof(float);
-    l.total = l.wt_off + (size_t)H * 4 * H * sizeof(float);
+    const size_t producers = (size_t)(H / units_per_cta(H));
+    l.total = l.bwd_ring_off + groups * 2 * producers * kGroup * (size_t)H * sizeof(float);
     return l;
 }
 
@@ -602,13 +662,10 @@ int launch_fwd(FwdParams p, int64_t B, cudaStream_t stream) {
 template <int KPT, int RG>
 int launch_bwd(BwdParams p, int64_t B, cudaStream_t stream) {
     constexpr int H = 32 * KPT;
-    const size_t smem = (size_t)kGroup * 4 * H * sizeof(float);
-    int dev = 0, sms = 0, per_sm = 0;
-    OPN_CUDA(cudaGetDevice(&dev));
-    OPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    OPN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<KPT, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_kernel<KPT, RG>, kThreads * RG, smem));
-    const int cap = sms * per_sm;
+    const size_t smem = 0;
+    int cap = 0;
+    int rc = max_coresident(lstm_bwd_kernel<KPT, RG>, kThreads * RG, smem, &cap);
+    if (rc != OPN_OK) return rc;
     const int n_slices = H / (kUnits * RG);
     const int groups = (int)((B + kGroup - 1) / kGroup);
     const int per_launch = cap / n_slices;
@@ -693,16 +750,9 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     cudaStream_t s = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
     OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, 4096, s));
-    OPN_CUDA(cudaMemsetAsync(ws + l.bwd_ring_off, 0, l.wt_off - l.bwd_ring_off, s));
-    float* w_t = reinterpret_cast<float*>(ws + l.wt_off);
-    {
-        dim3 grid((unsigned)((H + 31) / 32), (unsigned)((4 * H + 31) / 32));
-        transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(w_hh, w_t, (int)(4 * H), (int)H);
-        OPN_CUDA(cudaGetLastError());
-        count_launch();
-    }
+    OPN_CUDA(cudaMemsetAsync(ws + l.bwd_ring_off, 0, l.total - l.bwd_ring_off, s));
     BwdParams p;
-    p.w_t = w_t;
+    p.w_hh = w_hh;
     p.gates = gates;
     p.cells = cells;
     p.dh_out = dh_out;
@@ -714,10 +764,6 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     p.group_offset = 0;
     p.n_slices = 0;
     p.flags = debug_flags();
-    {
-        const char* e = getenv("OPN_LSTM_BWD_RG");
-        if (H == 512 && e && e[0] == '1') return launch_bwd<16, 1>(p, B, s);
-    }
     switch (H) {
         case 32: return launch_bwd<1, 1>(p, B, s);
         case 64: return launch_bwd<2, 1>(p, B, s);
