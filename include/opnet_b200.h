@@ -51,17 +51,16 @@ OPN_API int opn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N], optional ReLU.
  *   trans_a == 0: A is [M,K] row-major (lda);  trans_a != 0: A is [K,M] row-major
  *   trans_b == 0: B is [K,N] row-major (ldb);  trans_b != 0: B is [N,K] row-major
- *   beta must be 0 or 1; bias may be NULL.
- *   seg_len > 0 (only with trans_a != 0 && trans_b == 0): the K index is split as
- *   k = s*seg_len + j and row k of A/B lives at  base + s*seg_stride_{a,b} + j*ld{a,b}
- *   (used to pair dgates[b,t] with h[b,t-1] without crossing video boundaries).
+ *   beta must be 0 or 1; bias may be NULL.  lda/ldb/ldc are arbitrary row strides (>= the row length),
+ *   which is how strided row sets are contracted (e.g. slot 0 of every frame, or the last frame of
+ *   every video).
  * Replaces: nn.Linear / nn.LSTM input projections and every autograd matmul behind them
  *   (baselines/learned_models.py:30,33,39,46,47,67,69,70,83,84,100,102,113,116,130,133,
  *    139,146,149,167,172,178,184,192,195).
  */
 OPN_API int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
               const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int relu,
-              int64_t seg_len, int64_t seg_stride_a, int64_t seg_stride_b, void* stream);
+              void* stream);
 
 /* ---- persistent LSTM recurrence ---------------------------------------------------
  * One bias-free, unidirectional LSTM layer with zero initial state, PyTorch gate order

@@ -28,20 +28,9 @@ struct GemmParams {
     int relu;
     int k_per_split;  // multiple of BK
     int atomic_out;
-    long long seg_len, seg_stride_a, seg_stride_b;
 };
 
-template <bool SEG>
-__device__ __forceinline__ long long k_row_offset(int k, long long ld, long long seg_len, long long seg_stride) {
-    if (SEG) {
-        const long long s = k / seg_len;
-        const long long j = k - s * seg_len;
-        return s * seg_stride + j * ld;
-    }
-    return (long long)k * ld;
-}
-
-template <int BN, bool TA, bool TB, bool SEG>
+template <int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmParams p) {
     constexpr int TN = BN / 16;          // micro-tile width
     constexpr int A_PER = BM * BK / GEMM_THREADS;  // 8
@@ -73,7 +62,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmParams p)
             const int gm = m_blk + m, gk = k0 + k;
             float v = 0.0f;
             if (gm < p.M && gk < k_end) {
-                if (TA) v = __ldg(p.A + k_row_offset<SEG>(gk, p.lda, p.seg_len, p.seg_stride_a) + gm);
+                if (TA) v = __ldg(p.A + (long long)gk * p.lda + gm);
                 else v = __ldg(p.A + (long long)gm * p.lda + gk);
             }
             a_reg[e] = v;
@@ -87,7 +76,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(const GemmParams p)
             float v = 0.0f;
             if (gn < p.N && gk < k_end) {
                 if (TB) v = __ldg(p.B + (long long)gn * p.ldb + gk);
-                else v = __ldg(p.B + k_row_offset<SEG>(gk, p.ldb, p.seg_len, p.seg_stride_b) + gn);
+                else v = __ldg(p.B + (long long)gk * p.ldb + gn);
             }
             b_reg[e] = v;
         }
@@ -182,21 +171,20 @@ __global__ void zero_strided_kernel(float* C, long long ldc, int M, int N) {
     if (i < (long long)M * N) C[(i / N) * ldc + (i % N)] = 0.0f;
 }
 
-template <int BN, bool TA, bool TB, bool SEG>
+template <int BN, bool TA, bool TB>
 int launch(const GemmParams& p, dim3 grid, cudaStream_t s) {
-    sgemm_kernel<BN, TA, TB, SEG><<<grid, GEMM_THREADS, 0, s>>>(p);
+    sgemm_kernel<BN, TA, TB><<<grid, GEMM_THREADS, 0, s>>>(p);
     OPN_CUDA(cudaGetLastError());
     count_launch();
     return OPN_OK;
 }
 
 template <int BN>
-int dispatch(const GemmParams& p, bool ta, bool tb, bool seg, dim3 grid, cudaStream_t s) {
-    if (seg) return launch<BN, true, false, true>(p, grid, s);
-    if (!ta && !tb) return launch<BN, false, false, false>(p, grid, s);
-    if (!ta && tb) return launch<BN, false, true, false>(p, grid, s);
-    if (ta && !tb) return launch<BN, true, false, false>(p, grid, s);
-    return launch<BN, true, true, false>(p, grid, s);
+int dispatch(const GemmParams& p, bool ta, bool tb, dim3 grid, cudaStream_t s) {
+    if (!ta && !tb) return launch<BN, false, false>(p, grid, s);
+    if (!ta && tb) return launch<BN, false, true>(p, grid, s);
+    if (ta && !tb) return launch<BN, true, false>(p, grid, s);
+    return launch<BN, true, true>(p, grid, s);
 }
 
 }  // namespace
@@ -206,17 +194,13 @@ using namespace opn;
 
 extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                          int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
-                         const float* bias, int relu, int64_t seg_len, int64_t seg_stride_a, int64_t seg_stride_b,
-                         void* stream) {
+                         const float* bias, int relu, void* stream) {
     OPN_CHECK_ARG(M > 0 && N > 0 && K >= 0, "sgemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N,
                   (long long)K);
     OPN_CHECK_ARG(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "sgemm: dimension exceeds int32");
     OPN_CHECK_ARG(A && B && C, "sgemm: null pointer");
     OPN_CHECK_ARG(beta == 0.0f || beta == 1.0f, "sgemm: beta must be 0 or 1");
     const bool ta = trans_a != 0, tb = trans_b != 0;
-    const bool seg = seg_len > 0;
-    OPN_CHECK_ARG(!seg || (ta && !tb), "sgemm: segmented K requires trans_a=1, trans_b=0");
-    OPN_CHECK_ARG(!seg || (K % seg_len == 0), "sgemm: K must be a multiple of seg_len");
     cudaStream_t s = as_stream(stream);
 
     int dev = 0, sms = 148;
@@ -248,9 +232,6 @@ extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t
     p.relu = relu;
     p.k_per_split = k_per_split;
     p.atomic_out = splits > 1;
-    p.seg_len = seg ? seg_len : 1;
-    p.seg_stride_a = seg_stride_a;
-    p.seg_stride_b = seg_stride_b;
 
     if (splits > 1 && !p.beta_one) {
         const long long n = (long long)M * N;
@@ -259,7 +240,7 @@ extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t
         count_launch();
     }
     dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)splits);
-    if (bn == 128) return dispatch<128>(p, ta, tb, seg, grid, s);
-    if (bn == 64) return dispatch<64>(p, ta, tb, seg, grid, s);
-    return dispatch<16>(p, ta, tb, seg, grid, s);
+    if (bn == 128) return dispatch<128>(p, ta, tb, grid, s);
+    if (bn == 64) return dispatch<64>(p, ta, tb, grid, s);
+    return dispatch<16>(p, ta, tb, grid, s);
 }

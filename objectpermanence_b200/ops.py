@@ -49,17 +49,16 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # ------------------------------------------------------------------------------------------
 def sgemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a: bool, trans_b: bool, M: int, N: int,
           K: int, lda: int, ldb: int, ldc: int, alpha: float = 1.0, beta: float = 0.0,
-          bias: Optional[torch.Tensor] = None, relu: bool = False, seg: Optional[Tuple[int, int, int]] = None,
-          a_off: int = 0, b_off: int = 0, c_off: int = 0) -> None:
+          bias: Optional[torch.Tensor] = None, relu: bool = False, a_off: int = 0, b_off: int = 0,
+          c_off: int = 0) -> None:
     """out = alpha * op(a) op(b) + beta * out + bias.  Offsets are in elements."""
     if K == 0:
         if beta == 0.0:
             out.zero_()
         return
-    seg_len, seg_sa, seg_sb = seg if seg is not None else (0, 0, 0)
     rc = _lib.load().opn_sgemm(int(trans_a), int(trans_b), M, N, K, alpha, a.data_ptr() + 4 * a_off, lda,
                                b.data_ptr() + 4 * b_off, ldb, beta, out.data_ptr() + 4 * c_off, ldc, _ptr(bias),
-                               int(relu), seg_len, seg_sa, seg_sb, _stream())
+                               int(relu), _stream())
     _lib.check(rc, "opn_sgemm")
 
 
@@ -208,9 +207,13 @@ class LstmLayerFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dw_hh = torch.empty_like(w_hh)
             if T > 1:
-                # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1]: K runs over B segments of T-1 rows
-                sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B * (T - 1), lda=4 * H, ldb=H,
-                      ldc=H, seg=(T - 1, T * 4 * H, T * H), a_off=4 * H)
+                # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1].  Contract the flat row pairs (r+1, r) over all
+                # B*T-1 rows, then take out the B-1 pairs that straddle two videos (rows b*T and b*T-1).
+                sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B * T - 1, lda=4 * H, ldb=H,
+                      ldc=H, a_off=4 * H)
+                if B > 1:
+                    sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B - 1, lda=T * 4 * H,
+                          ldb=T * H, ldc=H, alpha=-1.0, beta=1.0, a_off=T * 4 * H, b_off=(T - 1) * H)
             else:
                 dw_hh.zero_()
         return dx, dw_ih, dw_hh

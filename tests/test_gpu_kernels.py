@@ -47,13 +47,16 @@ def test_sgemm_epilogue_and_split_k(cuda_device):
     assert (out2.cpu().double() - ref2).abs().max().item() <= 1e-5
 
 
-def test_sgemm_segmented_k_pairs_gates_with_previous_hidden(cuda_device):
+def test_sgemm_strided_rows_pair_gates_with_previous_hidden(cuda_device):
+    """dW_hh = sum_{b,t>=1} dgates[b,t]^T hs[b,t-1] as a flat contraction minus the video-straddling pairs."""
     B, T, G, H = 3, 7, 24, 8
     dg, hs = _rand((B, T, G), 10), _rand((B, T, H), 11)
     ref = torch.einsum("btg,bth->gh", dg[:, 1:].double(), hs[:, :-1].double())
     out = torch.empty(G, H, device=cuda_device)
-    ops.sgemm(dg.to(cuda_device), hs.to(cuda_device), out, trans_a=True, trans_b=False, M=G, N=H, K=B * (T - 1),
-              lda=G, ldb=H, ldc=H, seg=(T - 1, T * G, T * H), a_off=G)
+    dgd, hsd = dg.to(cuda_device), hs.to(cuda_device)
+    ops.sgemm(dgd, hsd, out, trans_a=True, trans_b=False, M=G, N=H, K=B * T - 1, lda=G, ldb=H, ldc=H, a_off=G)
+    ops.sgemm(dgd, hsd, out, trans_a=True, trans_b=False, M=G, N=H, K=B - 1, lda=T * G, ldb=T * H, ldc=H,
+              alpha=-1.0, beta=1.0, a_off=T * G, b_off=(T - 1) * H)
     assert (out.cpu().double() - ref).abs().max().item() <= 1e-5
 
 
