@@ -47,7 +47,12 @@ OPN_API unsigned long long opn_launch_count(void);
 /* SM count and compute capability of the current device */
 OPN_API int opn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
-/* ---- dense fp32 contraction (CUDA-core FFMA, fp32 accumulate) ---------------------
+/* ---- dense fp32 contraction ----------------------------------------------------------
+ * Two implementations behind one entry point: a CUDA-core FFMA kernel (any shape) and, for
+ * large shapes when the caller provides scratch, a tcgen05 tensor-core kernel that splits
+ * every fp32 operand into bf16 hi+lo and accumulates hi*hi + hi*lo + lo*hi in fp32 TMEM
+ * (relative operand error 2^-17).  opn_sgemm_workspace_bytes() returns the scratch size the
+ * tensor-core path wants for a shape, or 0 when the FFMA kernel will be used.
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N], optional ReLU.
  *   trans_a == 0: A is [M,K] row-major (lda);  trans_a != 0: A is [K,M] row-major
  *   trans_b == 0: B is [K,N] row-major (ldb);  trans_b != 0: B is [N,K] row-major
@@ -58,9 +63,10 @@ OPN_API int opn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   (baselines/learned_models.py:30,33,39,46,47,67,69,70,83,84,100,102,113,116,130,133,
  *    139,146,149,167,172,178,184,192,195).
  */
+OPN_API int64_t opn_sgemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 OPN_API int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
               const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int relu,
-              void* stream);
+              void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- persistent LSTM recurrence ---------------------------------------------------
  * One bias-free, unidirectional LSTM layer with zero initial state, PyTorch gate order

@@ -22,8 +22,9 @@ SIGNATURES = {
     "opn_last_error": (c_char_p, []),
     "opn_launch_count": (c_ulonglong, []),
     "opn_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "opn_sgemm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "opn_sgemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_float, _P, c_int64, _P, c_int64, c_float, _P,
-                          c_int64, _P, c_int, _P]),
+                          c_int64, _P, c_int, _P, c_int64, _P]),
     "opn_lstm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "opn_lstm_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "opn_lstm_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),

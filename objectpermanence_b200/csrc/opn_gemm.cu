@@ -7,9 +7,18 @@
 //
 // 128 x BN x 16 tiles, 256 threads, 8 x (BN/16) register micro-tiles, register-staged double
 // buffering, optional split-K (fp32 atomics) when the M x N grid alone cannot fill 148 SMs.
+#include <stdlib.h>
+
 #include "opn_common.cuh"
 
 namespace opn {
+
+// tensor-core path (opn_gemm_tc.cu)
+long long gemm_tc_workspace_bytes(long long M, long long N, long long K);
+int gemm_tc(int trans_a, int trans_b, long long M, long long N, long long K, float alpha, const float* A, long long lda,
+            const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int relu,
+            void* workspace, long long workspace_bytes, cudaStream_t s);
+
 namespace {
 
 constexpr int BM = 128;
@@ -187,14 +196,31 @@ int dispatch(const GemmParams& p, bool ta, bool tb, dim3 grid, cudaStream_t s) {
     return launch<BN, true, true>(p, grid, s);
 }
 
+// Shapes worth the operand pre-pass of the tcgen05 path: both output dims at least one half tile, a K of at least 256
+// to amortise it, and at least 2^27 multiply-adds.  OPN_GEMM_TC=0 forces the FFMA kernel everywhere.
+bool tc_eligible(int64_t M, int64_t N, int64_t K) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("OPN_GEMM_TC");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!enabled) return false;
+    return M >= 64 && N >= 64 && K >= 256 && (double)M * (double)N * (double)K >= 134217728.0;
+}
+
 }  // namespace
 }  // namespace opn
 
 using namespace opn;
 
+extern "C" int64_t opn_sgemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0 || !tc_eligible(M, N, K)) return 0;
+    return (int64_t)gemm_tc_workspace_bytes(M, N, K);
+}
+
 extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                          int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
-                         const float* bias, int relu, void* stream) {
+                         const float* bias, int relu, void* workspace, int64_t workspace_bytes, void* stream) {
     OPN_CHECK_ARG(M > 0 && N > 0 && K >= 0, "sgemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N,
                   (long long)K);
     OPN_CHECK_ARG(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "sgemm: dimension exceeds int32");
@@ -202,6 +228,10 @@ extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t
     OPN_CHECK_ARG(beta == 0.0f || beta == 1.0f, "sgemm: beta must be 0 or 1");
     const bool ta = trans_a != 0, tb = trans_b != 0;
     cudaStream_t s = as_stream(stream);
+    if (K > 0 && workspace != nullptr && tc_eligible(M, N, K) &&
+        workspace_bytes >= (int64_t)gemm_tc_workspace_bytes(M, N, K))
+        return gemm_tc(trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, relu, workspace,
+                       workspace_bytes, s);
 
     int dev = 0, sms = 148;
     OPN_CUDA(cudaGetDevice(&dev));

@@ -56,9 +56,12 @@ def sgemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, trans_a: bool,
         if beta == 0.0:
             out.zero_()
         return
-    rc = _lib.load().opn_sgemm(int(trans_a), int(trans_b), M, N, K, alpha, a.data_ptr() + 4 * a_off, lda,
-                               b.data_ptr() + 4 * b_off, ldb, beta, out.data_ptr() + 4 * c_off, ldc, _ptr(bias),
-                               int(relu), _stream())
+    lib = _lib.load()
+    ws_bytes = lib.opn_sgemm_workspace_bytes(M, N, K)   # > 0: the tcgen05 split-bf16 path will be taken
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device) if ws_bytes > 0 else None
+    rc = lib.opn_sgemm(int(trans_a), int(trans_b), M, N, K, alpha, a.data_ptr() + 4 * a_off, lda,
+                       b.data_ptr() + 4 * b_off, ldb, beta, out.data_ptr() + 4 * c_off, ldc, _ptr(bias),
+                       int(relu), _ptr(ws), ws_bytes, _stream())
     _lib.check(rc, "opn_sgemm")
 
 
