@@ -280,10 +280,16 @@ def run_ours(args):
                           "ffma_tflops": 2.0 * rows * 4 * H * H / (ms * 1e-3) / 1e12}
     dom = max(kern, key=lambda k: kern[k]["ms"])
     hbm_peak = float(peaks["hbm_gbs"])
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    tpath = os.path.join(REPO, "profiles", "r01_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "note": "recurrence is FP32-FFMA / step-latency bound (arithmetic intensity ~260 FLOP/B), "
-                        "see DESIGN.md section 5; per-kernel detail in 'kernels'",
+                "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "the persistent recurrences are step-latency bound (300 dependent steps, inter-CTA exchange "
+                        "1-1.3 us/step) with the FP32 FMA pipe behind it, not HBM bound: DESIGN.md section 3.1/5; "
+                        "per-kernel detail in 'kernels'",
                 "whole_step_algorithmic_gbs": (31700.0 * B_PER_GPU * T + 17.05e6) / (ms_per_step * 1e-3) / 1e9}
 
     # CPU baseline: bounded sample of the same workload on the host cores
