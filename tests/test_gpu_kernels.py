@@ -60,6 +60,49 @@ def test_sgemm_strided_rows_pair_gates_with_previous_hidden(cuda_device):
     assert (out.cpu().double() - ref).abs().max().item() <= 1e-5
 
 
+# ---- tcgen05 split-bf16 path of opn_sgemm ---------------------------------------------------------
+def _tc_expected(M, N, K):
+    return _lib.load().opn_sgemm_workspace_bytes(M, N, K) > 0
+
+
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 8192), (200, 140, 5000), (1000, 777, 555), (2048, 512, 1279)])
+def test_sgemm_tensor_core_path(cuda_device, ta, tb, M, N, K):
+    """Shapes above the tensor-core threshold: odd sizes (padding), split-K (small grids), all layouts."""
+    assert _tc_expected(M, N, K)
+    a = _rand((K, M) if ta else (M, K), 21)
+    b = _rand((N, K) if tb else (K, N), 22)
+    ref = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    out = torch.full((M, N), float("nan"), device=cuda_device)
+    ops.sgemm(a.to(cuda_device), b.to(cuda_device), out, trans_a=ta, trans_b=tb, M=M, N=N, K=K, lda=a.shape[1],
+              ldb=b.shape[1], ldc=N)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    # split-bf16 operands (2^-17) + truncating tensor-core accumulation: relative to the largest entry
+    assert (got - ref).abs().max().item() <= 5e-5 * ref.abs().max().item()
+
+
+def test_sgemm_tensor_core_epilogue(cuda_device):
+    M, N, K = 384, 256, 2048
+    assert _tc_expected(M, N, K)
+    a, b, bias, c0 = _rand((M, K), 23), _rand((N, K), 24), _rand((N,), 25), _rand((M, N), 26)
+    ad, bd = a.to(cuda_device), b.to(cuda_device)
+    prod = a.double() @ b.double().t()
+    # alpha, beta = 1, bias (split-K with atomics: 6 tiles only)
+    out = c0.clone().to(cuda_device)
+    ops.sgemm(ad, bd, out, trans_a=False, trans_b=True, M=M, N=N, K=K, lda=K, ldb=K, ldc=N, alpha=-0.5, beta=1.0,
+              bias=bias.to(cuda_device))
+    ref = -0.5 * prod + c0.double() + bias.double()
+    assert (out.cpu().double() - ref).abs().max().item() <= 5e-5 * prod.abs().max().item()
+    # bias + ReLU (no split-K allowed with ReLU), strided output
+    big = torch.full((M, N + 8), 7.0, device=cuda_device)
+    ops.sgemm(ad, bd, big, trans_a=False, trans_b=True, M=M, N=N, K=K, lda=K, ldb=K, ldc=N + 8,
+              bias=bias.to(cuda_device), relu=True)
+    ref2 = torch.relu(prod + bias.double())
+    assert (big[:, :N].cpu().double() - ref2).abs().max().item() <= 5e-5 * prod.abs().max().item()
+    assert (big[:, N:] == 7.0).all()
+
+
 # ---- persistent LSTM ------------------------------------------------------------------------
 def _lstm_case(B, T, I, H, seed, scale=1.0):
     x = _rand((B, T, I), seed, 1.0)

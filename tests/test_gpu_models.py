@@ -125,6 +125,19 @@ def test_transformer_lstm_shipped_config_small_batch(cuda_device):
     _oracle_vs_module("transformer_lstm", cfg, 2, 300, cuda_device, seed=8, grad_tol=5e-4)
 
 
+def test_transformer_lstm_tensor_core_attention(cuda_device):
+    """S = B*T = 2400: P*V, the FFN and the LSTM input projections take the tcgen05 path."""
+    cfg = {"boxes_features_dim": 256, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2,
+           "lstm_hidden_dim": 512}
+    _oracle_vs_module("transformer_lstm", cfg, 8, 300, cuda_device, seed=9, grad_tol=5e-4)
+
+
+def test_non_linear_lstm_shipped_config(cuda_device):
+    """K = 3840 input projection of the shipped non_linear_lstm config on the tensor-core path."""
+    _oracle_vs_module("non_linear_lstm", {"boxes_features_dim": 256, "videos_hidden_dim": 512}, 8, 100, cuda_device,
+                      seed=10, grad_tol=5e-4)
+
+
 def test_mean_iou_parity_on_256_videos(cuda_device):
     """mean IoU equal to 3 decimals through the reference's own post-processing
     (x[320,240,320,240] -> int32 -> IoU with the +1 pixel convention), >= 256 videos."""
