@@ -196,7 +196,7 @@ int dispatch(const GemmParams& p, bool ta, bool tb, dim3 grid, cudaStream_t s) {
     return launch<BN, true, true>(p, grid, s);
 }
 
-// Shapes worth the operand pre-pass of the tcgen05 path: both output dims at least one half tile, a K of at least 256
+// Shapes worth the operand pre-pass of the tcgen05 path: both output dims at least one half tile, a K of at least 64
 // to amortise it, and at least 2^27 multiply-adds.  OPN_GEMM_TC=0 forces the FFMA kernel everywhere.
 bool tc_eligible(int64_t M, int64_t N, int64_t K) {
     static int enabled = -1;
@@ -205,7 +205,12 @@ bool tc_eligible(int64_t M, int64_t N, int64_t K) {
         enabled = (e && e[0] == '0') ? 0 : 1;
     }
     if (!enabled) return false;
-    return M >= 64 && N >= 64 && K >= 256 && (double)M * (double)N * (double)K >= 134217728.0;
+    static long long min_k = -1;
+    if (min_k < 0) {
+        const char* e = getenv("OPN_GEMM_TC_MINK");   // tuning knob
+        min_k = e ? atoll(e) : 64;
+    }
+    return M >= 64 && N >= 64 && K >= min_k && (double)M * (double)N * (double)K >= 134217728.0;
 }
 
 }  // namespace
