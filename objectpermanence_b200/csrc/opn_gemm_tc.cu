@@ -7,16 +7,22 @@
 // TMEM accumulator: three kind::f16 MMAs per K=16 slice, relative operand error 2^-17.  This keeps the
 // 1e-4 fp32 parity bound of the hot path through K = 9600 reductions where a single bf16/tf32 pass does not.
 //
-// Structure (one CTA = one 128 x 128 output tile, 128 threads):
+// Structure (persistent, warp specialised; 192 threads, one CTA per SM):
 //   * a pre-pass kernel converts (and, if needed, transposes) each operand once into zero-padded K-major
 //     bf16 hi / lo matrices;
-//   * the GEMM kernel streams 128 x 64 tiles of the four matrices with cp.async (16-byte chunks written in
-//     the SWIZZLE_128B K-major canonical layout the UMMA shared-memory descriptor expects) through a
-//     3-stage ring; one thread issues tcgen05.mma (cta_group::1, M=128, N=128, K=16) and tcgen05.commit
-//     signals an mbarrier when a stage may be overwritten;
-//   * the accumulator lives in 128 TMEM columns; the four warps read it back with tcgen05.ld (32 lanes x
-//     32 columns per instruction) and apply the epilogue; split-K partial tiles are added with fp32 atomics.
+//   * warp 0 (one lane) is the TMA producer: per 64-wide k-block four cp.async.bulk.tensor.2d loads bring the
+//     128 x 64 tiles of Ahi, Alo, Bhi, Blo into a 3-stage shared-memory ring in the SWIZZLE_128B K-major layout
+//     the UMMA descriptors expect (full / empty mbarriers per stage);
+//   * warp 1 (one lane) issues tcgen05.mma (cta_group::1, M=128, N=128, K=16, kind::f16), twelve per k-block;
+//     tcgen05.commit releases the stage and, after the last k-block, hands the accumulator to the epilogue;
+//   * the accumulator is double buffered in TMEM (2 x 128 columns), so warps 2-5 read tile i back with
+//     tcgen05.ld, transpose it through a small per-warp shared tile and write 128-byte rows of C while the
+//     mainloop of tile i+1 is already running; split-K partial tiles are added with fp32 atomics.
+// The first version (cp.async by all threads + a CTA barrier per k-block, one tile per CTA) reached 11-13 %
+// tensor-pipe activity (profiles/r01_gemm_tc_ncu_summary.csv).
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS, vendored headers, read-only reference).
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
 #include "opn_common.cuh"
@@ -25,10 +31,11 @@ namespace opn {
 namespace {
 
 constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3;
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 192;                     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int TILE_BYTES = TBM * TBK * 2;           // 16 KB, one operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // Ahi, Alo, Bhi, Blo
-constexpr int TC_SMEM = TSTAGES * STAGE_BYTES + 1024;  // + alignment slack
+constexpr int EPI_PITCH = 33;                       // per-warp 32 x 32 transpose tile, conflict free
+constexpr int TC_SMEM = TSTAGES * STAGE_BYTES + 4 * 32 * EPI_PITCH * 4 + 1024;  // + alignment slack
 
 // ---- pre-pass: fp32 -> (hi, lo) bf16, K-major, zero padded ---------------------------------------------------
 // dst[r][k] for r < rows_pad, k < k_pad;  source element (r, k) is src[r*ld + k] or, transposed, src[k*ld + r].
@@ -92,124 +99,138 @@ __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.f
 
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     // bounded spin: a broken pipeline must not hang the GPU
-    for (unsigned int i = 0; i < (1u << 26); ++i)
+    for (unsigned int i = 0; i < (1u << 22); ++i)
         if (mbar_try_wait(bar, parity)) return;
 }
 
 struct TcParams {
-    const __nv_bfloat16* a_hi;
-    const __nv_bfloat16* a_lo;
-    const __nv_bfloat16* b_hi;
-    const __nv_bfloat16* b_lo;
     float* C;
     const float* bias;
     long long ldc;
-    int M, N, k_pad;       // true M, N; padded K (multiple of 64)
-    int kb_per_split;      // k-blocks (of 64) per split
+    int M, N;
+    int tiles_m, tiles_n, splits;
+    int nkb_total;         // k-blocks of 64 in the padded K
+    int kb_per_split;
     float alpha;
     int beta_one, relu, atomic_out;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams p) {
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t mma_done[TSTAGES];
+    __shared__ __align__(8) uint64_t full_bar[TSTAGES], empty_bar[TSTAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // 1024-byte aligned tile ring (SWIZZLE_128B atoms are 8 rows x 128 B)
-    const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-
-    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
-    const int nkb_total = p.k_pad / TBK;
-    const int kb_begin = blockIdx.z * p.kb_per_split;
-    const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
-    const int nkb = kb_end - kb_begin;
+    const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // 1024-byte aligned (SWIZZLE_128B atoms)
+    float* epi_s = reinterpret_cast<float*>(smem_dyn + (ring - smem_u32(smem_dyn)) + TSTAGES * STAGE_BYTES);
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < TSTAGES; ++s) mbar_init(&mma_done[s], 1);
+        for (int s = 0; s < TSTAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);   // one arrival per epilogue warp
+        }
         mbar_fence_init();
     }
-    if (warp == 0) {  // TMEM: 128 fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128)
+    if (warp == 1) {  // TMEM: two 128-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_acc = tmem_base_s;
+    const uint32_t tmem_base = tmem_base_s;
 
-    // one stage = 4 tiles of [128 rows][64 bf16]; 16-byte chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)
-    auto load_stage = [&](int stage, int kb) {
-        const uint32_t sbase = ring + stage * STAGE_BYTES;
-        const long long kofs = (long long)kb * TBK;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const int idx = tid + TC_THREADS * i;     // 0 .. 4095
-            const int t = idx >> 10;                  // tile: 0 Ahi, 1 Alo, 2 Bhi, 3 Blo
-            const int r = (idx >> 3) & 127, c = idx & 7;
-            const __nv_bfloat16* base = (t == 0) ? p.a_hi : (t == 1) ? p.a_lo : (t == 2) ? p.b_hi : p.b_lo;
-            const int row = ((t < 2) ? m0 : n0) + r;
-            const __nv_bfloat16* src = base + (long long)row * p.k_pad + kofs + 8 * c;
-            const uint32_t dst = sbase + t * TILE_BYTES + r * 128 + ((c ^ (r & 7)) << 4);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        }
-    };
+    const int n_work = p.tiles_m * p.tiles_n * p.splits;
 
-    if (nkb > 0) {
-#pragma unroll
-        for (int s = 0; s < TSTAGES - 1; ++s) {
-            if (s < nkb) load_stage(s, kb_begin + s);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int stage = kb % TSTAGES;
-            asm volatile("cp.async.wait_group %0;" ::"n"(TSTAGES - 2) : "memory");
-            fence_proxy_async_smem();   // cp.async / generic writes -> tensor-core (async proxy) reads
-            __syncthreads();
-            // queue this k-block's MMAs first (the tensor pipe runs them in order behind k-block kb-1) ...
-            if (tid == 0) {
-                tcgen05_fence_after();
-                const uint32_t sbase = ring + stage * STAGE_BYTES;
-#pragma unroll
-                for (int k16 = 0; k16 < TBK / 16; ++k16) {
-                    const uint64_t ah = make_smem_desc_sw128(sbase + 0 * TILE_BYTES + k16 * 32);
-                    const uint64_t al = make_smem_desc_sw128(sbase + 1 * TILE_BYTES + k16 * 32);
-                    const uint64_t bh = make_smem_desc_sw128(sbase + 2 * TILE_BYTES + k16 * 32);
-                    const uint64_t bl = make_smem_desc_sw128(sbase + 3 * TILE_BYTES + k16 * 32);
-                    umma_bf16(tmem_acc, ah, bh, (kb > 0 || k16 > 0) ? 1u : 0u);
-                    umma_bf16(tmem_acc, ah, bl, 1u);
-                    umma_bf16(tmem_acc, al, bh, 1u);
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w % p.splits, tile = w / p.splits;
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait_spin(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    const uint32_t sbase = ring + stage * STAGE_BYTES;
+                    tma_load_2d(sbase + 0 * TILE_BYTES, &map_ahi, kb * TBK, tm * TBM, &full_bar[stage]);
+                    tma_load_2d(sbase + 1 * TILE_BYTES, &map_alo, kb * TBK, tm * TBM, &full_bar[stage]);
+                    tma_load_2d(sbase + 2 * TILE_BYTES, &map_bhi, kb * TBK, tn * TBN, &full_bar[stage]);
+                    tma_load_2d(sbase + 3 * TILE_BYTES, &map_blo, kb * TBK, tn * TBN, &full_bar[stage]);
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&mma_done[stage]);   // implies tcgen05.fence::before_thread_sync
             }
-            // ... then refill the stage k-block kb-1 used, once its MMAs have drained
-            const int next = kb + TSTAGES - 1;
-            if (next < nkb) {
-                if (kb >= 1) mbar_wait_spin(&mma_done[(kb - 1) % TSTAGES], (uint32_t)(((kb - 1) / TSTAGES) & 1));
-                load_stage(next % TSTAGES, kb_begin + next);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        // all MMAs are complete when the last commit has arrived
-        mbar_wait_spin(&mma_done[(nkb - 1) % TSTAGES], (uint32_t)(((nkb - 1) / TSTAGES) & 1));
-        tcgen05_fence_after();
-    }
-
-    // ---- epilogue: TMEM -> registers -> padded shared tile -> coalesced rows of C ---------------------------
-    // (all MMAs have completed, so the operand ring is free: the 128 x 128 fp32 tile is staged there with a
-    //  row pitch of 132 floats, which makes both the per-row STS.128 of the TMEM read-out and the per-row
-    //  LDS.128 of the write-out conflict free)
-    constexpr int EP = TBN + 4;
-    float* tile_s = reinterpret_cast<float*>(smem_dyn + (ring - smem_u32(smem_dyn)));
-    {
-        const int r = warp * 32 + lane;  // warp w may only touch TMEM lanes [32w, 32w+32)
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb_total, kb0 + p.kb_per_split);
+                mbar_wait_spin(&tmem_empty[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * TBN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait_spin(&full_bar[stage], phase);          // TMA bytes have landed
+                    tcgen05_fence_after();
+                    const uint32_t sbase = ring + stage * STAGE_BYTES;
+#pragma unroll
+                    for (int k16 = 0; k16 < TBK / 16; ++k16) {
+                        const uint64_t ah = make_smem_desc_sw128(sbase + 0 * TILE_BYTES + k16 * 32);
+                        const uint64_t al = make_smem_desc_sw128(sbase + 1 * TILE_BYTES + k16 * 32);
+                        const uint64_t bh = make_smem_desc_sw128(sbase + 2 * TILE_BYTES + k16 * 32);
+                        const uint64_t bl = make_smem_desc_sw128(sbase + 3 * TILE_BYTES + k16 * 32);
+                        umma_bf16(tmem_acc, ah, bh, (kb > kb0 || k16 > 0) ? 1u : 0u);
+                        umma_bf16(tmem_acc, ah, bl, 1u);
+                        umma_bf16(tmem_acc, al, bh, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);                  // stage may be refilled when these retire
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full[acc]);                        // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue warps (2..5): TMEM lane quadrant = warp % 4 =================
+        const int q = warp & 3;
+        float* my_s = epi_s + (warp - 2) * 32 * EPI_PITCH;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w % p.splits, tile = w / p.splits;
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int m0 = tm * TBM + q * 32, n0 = tn * TBN;
+            const bool lead = (split == 0);
+            mbar_wait_spin(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
 #pragma unroll 1
-        for (int col = 0; col < TBN; col += 32) {
-            uint32_t v[32];
-            if (nkb > 0) {
-                const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)col;
+            for (int col = 0; col < TBN; col += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TBN + col);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -220,69 +241,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const TcParams p
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4*>(&tile_s[r * EP + col + j]) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-    }
-    __syncthreads();
-    {
-        const bool lead = (blockIdx.z == 0);
-        const int n = n0 + 4 * lane;           // this lane's 4 columns
-        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (n + 3 < p.N);
-        float b4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias && (!p.atomic_out || lead)) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (n + j < p.N) b4[j] = p.bias[n + j];
-        }
-        for (int r = warp; r < TBM; r += 4) {   // one warp writes one 512-byte row per iteration
-            const int m = m0 + r;
-            if (m >= p.M) break;
-            const float4 t = *reinterpret_cast<const float4*>(&tile_s[r * EP + 4 * lane]);
-            float x[4] = {p.alpha * t.x + b4[0], p.alpha * t.y + b4[1], p.alpha * t.z + b4[2], p.alpha * t.w + b4[3]};
-            float* c = p.C + (long long)m * p.ldc + n;
-            if (p.atomic_out) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (n + j < p.N) atomicAdd(c + j, x[j]);
-            } else if (vec_ok) {
-                if (p.beta_one) {
-                    const float4 o = *reinterpret_cast<const float4*>(c);
-                    x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+                if (col + 32 == TBN) {  // last read of this accumulator: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                if (p.relu) {
+                // lane = row: transpose through shared memory so that a warp store covers one 128-byte row segment
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
-                }
-                *reinterpret_cast<float4*>(c) = make_float4(x[0], x[1], x[2], x[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (n + j < p.N) {
-                        float y = x[j];
-                        if (p.beta_one) y += c[j];
-                        if (p.relu) y = fmaxf(y, 0.0f);
-                        c[j] = y;
+                for (int j = 0; j < 32; ++j) my_s[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int n = n0 + col + lane;
+                float bias_v = 0.0f;
+                if (p.bias && n < p.N && (!p.atomic_out || lead)) bias_v = p.bias[n];
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int m = m0 + r;
+                    if (m < p.M && n < p.N) {
+                        float x = p.alpha * my_s[r * EPI_PITCH + lane] + bias_v;
+                        float* c = p.C + (long long)m * p.ldc + n;
+                        if (p.atomic_out) {
+                            atomicAdd(c, x);
+                        } else {
+                            if (p.beta_one) x += *c;
+                            if (p.relu) x = fmaxf(x, 0.0f);
+                            *c = x;
+                        }
                     }
                 }
+                __syncwarp();
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(128) : "memory");
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
 __global__ void zero_strided_tc_kernel(float* C, long long ldc, int M, int N) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (long long)M * N) C[(i / N) * ldc + (i % N)] = 0.0f;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+PFN_cuTensorMapEncodeTiled get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows][k_pad] (K contiguous), box = 64 (K) x 128 (rows), 128-byte swizzle
+int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, long long rows, long long k_pad) {
+    PFN_cuTensorMapEncodeTiled encode = get_encode_fn();
+    if (!encode) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available");
+        return OPN_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)k_pad * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return OPN_ERR_CUDA;
+    }
+    return OPN_OK;
 }
 
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
@@ -334,10 +368,18 @@ int gemm_tc(int trans_a, int trans_b, long long M, long long N, long long K, flo
     const int kb_per_split = (nkb + splits - 1) / splits;
     splits = (nkb + kb_per_split - 1) / kb_per_split;
 
+    CUtensorMap map_ahi, map_alo, map_bhi, map_blo;
+    int rc;
+    if ((rc = make_operand_map(&map_ahi, a_hi, mp, kp)) != OPN_OK) return rc;
+    if ((rc = make_operand_map(&map_alo, a_lo, mp, kp)) != OPN_OK) return rc;
+    if ((rc = make_operand_map(&map_bhi, b_hi, np, kp)) != OPN_OK) return rc;
+    if ((rc = make_operand_map(&map_blo, b_lo, np, kp)) != OPN_OK) return rc;
+
     TcParams p;
-    p.a_hi = a_hi; p.a_lo = a_lo; p.b_hi = b_hi; p.b_lo = b_lo;
     p.C = C; p.bias = bias; p.ldc = ldc;
-    p.M = (int)M; p.N = (int)N; p.k_pad = (int)kp;
+    p.M = (int)M; p.N = (int)N;
+    p.tiles_m = gm; p.tiles_n = gn; p.splits = splits;
+    p.nkb_total = nkb;
     p.kb_per_split = kb_per_split;
     p.alpha = alpha;
     p.beta_one = beta == 1.0f;
@@ -349,8 +391,10 @@ int gemm_tc(int trans_a, int trans_b, long long M, long long N, long long K, flo
         OPN_CUDA(cudaGetLastError());
         count_launch();
     }
+    const int n_work = gm * gn * splits;
+    const int grid = n_work < sms ? n_work : sms;
     OPN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    gemm_tc_kernel<<<dim3((unsigned)gn, (unsigned)gm, (unsigned)splits), TC_THREADS, TC_SMEM, s>>>(p);
+    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(map_ahi, map_alo, map_bhi, map_blo, p);
     OPN_CUDA(cudaGetLastError());
     count_launch();
     return OPN_OK;
