@@ -19,7 +19,7 @@
 //     tcgen05.ld, transpose it through a small per-warp shared tile and write 128-byte rows of C while the
 //     mainloop of tile i+1 is already running; split-K partial tiles are added with fp32 atomics.
 // The first version (cp.async by all threads + a CTA barrier per k-block, one tile per CTA) reached 11-13 %
-// tensor-pipe activity (profiles/r01_gemm_tc_ncu_summary.csv).
+// tensor-pipe activity (profiles/r01_gemm_tc_v1_ncu_summary.csv).
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS, vendored headers, read-only reference).
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -34,7 +34,7 @@ constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3;
 constexpr int TC_THREADS = 192;                     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int TILE_BYTES = TBM * TBK * 2;           // 16 KB, one operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;         // Ahi, Alo, Bhi, Blo
-constexpr int EPI_PITCH = 33;                       // per-warp 32 x 32 transpose tile, conflict free
+constexpr int EPI_PITCH = 36;                       // per-warp 32 x 32 transpose tile: 16-byte aligned rows, conflict free
 constexpr int TC_SMEM = TSTAGES * STAGE_BYTES + 4 * 32 * EPI_PITCH * 4 + 1024;  // + alignment slack
 
 // ---- pre-pass: fp32 -> (hi, lo) bf16, K-major, zero padded ---------------------------------------------------
@@ -246,25 +246,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                // lane = row: transpose through shared memory so that a warp store covers one 128-byte row segment
+                // lane = row: transpose through shared memory so that a warp store covers whole 128-byte row segments
 #pragma unroll
-                for (int j = 0; j < 32; ++j) my_s[lane * EPI_PITCH + j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(&my_s[lane * EPI_PITCH + j]) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                const int n = n0 + col + lane;
-                float bias_v = 0.0f;
-                if (p.bias && n < p.N && (!p.atomic_out || lead)) bias_v = p.bias[n];
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
+                const int nq = n0 + col + 4 * (lane & 7);          // this lane's 4 columns
+                const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (nq + 3 < p.N);
+                float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (p.bias && (!p.atomic_out || lead)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (nq + j < p.N) b4[j] = p.bias[nq + j];
+                }
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 4) {               // 4 rows x 128 bytes per warp instruction
+                    const int r = rr + (lane >> 3);
                     const int m = m0 + r;
-                    if (m < p.M && n < p.N) {
-                        float x = p.alpha * my_s[r * EPI_PITCH + lane] + bias_v;
-                        float* c = p.C + (long long)m * p.ldc + n;
+                    const float4 t = *reinterpret_cast<const float4*>(&my_s[r * EPI_PITCH + 4 * (lane & 7)]);
+                    if (m < p.M && nq < p.N) {
+                        float x[4] = {p.alpha * t.x + b4[0], p.alpha * t.y + b4[1], p.alpha * t.z + b4[2], p.alpha * t.w + b4[3]};
+                        float* c = p.C + (long long)m * p.ldc + nq;
                         if (p.atomic_out) {
-                            atomicAdd(c, x);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (nq + j < p.N) atomicAdd(c + j, x[j]);
+                        } else if (vec_ok) {
+                            if (p.beta_one) {
+                                const float4 o = *reinterpret_cast<const float4*>(c);
+                                x[0] += o.x; x[1] += o.y; x[2] += o.z; x[3] += o.w;
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
+                            }
+                            *reinterpret_cast<float4*>(c) = make_float4(x[0], x[1], x[2], x[3]);
                         } else {
-                            if (p.beta_one) x += *c;
-                            if (p.relu) x = fmaxf(x, 0.0f);
-                            *c = x;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (nq + j < p.N) {
+                                    float y = x[j];
+                                    if (p.beta_one) y += c[j];
+                                    if (p.relu) y = fmaxf(y, 0.0f);
+                                    c[j] = y;
+                                }
+                            }
                         }
                     }
                 }
