@@ -63,35 +63,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-// dst/src 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// order generic-proxy accesses against async-proxy (TMA) accesses.  The state-space
-// qualified forms matter: plain fence.proxy.async compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC,
-// the .global form to a bare FENCE.VIEW.ASYNC.G (checked with cuobjdump -sass).
-__device__ __forceinline__ void fence_proxy_async_global() {
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-}
+// order generic-proxy accesses against async-proxy (TMA / tensor-core) accesses.  The state-space qualified
+// forms matter: plain fence.proxy.async compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC (checked with
+// cuobjdump -sass), the .shared::cta form to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC.S.
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// gpu-scope release increment / acquire load for the inter-CTA step counters
-__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -53,7 +53,6 @@ struct FwdParams {
     int B, T;
     int group_offset;  // first batch group handled by this launch
     int n_slices;      // H / 8
-    int flags;         // debug knobs (OPN_LSTM_* environment): bit1 fence after publish, bit2 progress marks
 };
 
 struct BwdParams {
@@ -67,7 +66,6 @@ struct BwdParams {
     int B, T;
     int group_offset;
     int n_slices;
-    int flags;
 };
 
 // parity carried by the words of step t: slot t&1 is rewritten every 2 steps, so the bit
@@ -229,16 +227,6 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[64], int lane) 
     butterfly_stage<4, 1, 64>(v, (lane & 1) != 0, 1);
 }
 
-// Sum v[16] over the 32 lanes.  On return v[0] of lane l is the total of index l >> 1 (both lanes of a pair
-// hold it).
-__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
-    butterfly_stage<16, 3, 16>(v, (lane & 16) != 0, 16);
-    butterfly_stage<8, 2, 16>(v, (lane & 8) != 0, 8);
-    butterfly_stage<4, 1, 16>(v, (lane & 4) != 0, 4);
-    butterfly_stage<2, 0, 16>(v, (lane & 2) != 0, 2);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 // ------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------
@@ -352,7 +340,6 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
         if (valid) {
             // critical path first: publish h_t to the other CTAs of this batch group
             if (gh == 0 && t + 1 < T) st_flagged(ring + (size_t)(t & 1) * (kGroup * H) + bl * H + u, hval, step_parity(t));
-            if (p.flags & 2) __threadfence();
             const size_t row = row0 + t;
             if (gh == 0) {
                 p.hs[row * H + u] = hval;
@@ -605,19 +592,11 @@ WorkspaceLayout layout(int64_t B, int64_t T, int64_t H) {
     const size_t groups = (size_t)((B + kGroup - 1) / kGroup);
     WorkspaceLayout l;
     l.status_off = 0;
-    l.fwd_ring_off = 4096;  // status block: 4 words + per-CTA progress marks (debug)
+    l.fwd_ring_off = 4096;  // status block (4 words used)
     l.bwd_ring_off = l.fwd_ring_off + groups * 2 * kGroup * (size_t)H * sizeof(float);
     const size_t producers = (size_t)(H / units_per_cta(H));
     l.total = l.bwd_ring_off + groups * 2 * producers * kGroup * (size_t)H * sizeof(float);
     return l;
-}
-
-int debug_flags() {
-    int f = 0;
-    const char* e;
-    if ((e = getenv("OPN_LSTM_FENCE")) && e[0] == '1') f |= 2;
-    if ((e = getenv("OPN_LSTM_PROGRESS")) && e[0] == '1') f |= 4;
-    return f;
 }
 
 bool supported_hidden(int64_t H) { return H == 32 || H == 64 || H == 128 || H == 256 || H == 512; }
@@ -722,7 +701,6 @@ extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj,
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
-    p.flags = debug_flags();
     switch (H) {
         case 32: return launch_fwd<1, 1>(p, B, s);
         case 64: return launch_fwd<2, 1>(p, B, s);
@@ -763,7 +741,6 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
-    p.flags = debug_flags();
     switch (H) {
         case 32: return launch_bwd<1, 1>(p, B, s);
         case 64: return launch_bwd<2, 1>(p, B, s);
