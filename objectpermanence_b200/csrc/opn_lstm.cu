@@ -29,125 +29,11 @@
 // all CTAs leave the time loop (no hang, no trap).
 #include <stdlib.h>
 
-#include "opn_common.cuh"
+#include "opn_lstm_common.cuh"
 
 namespace opn {
 
 namespace {
-
-constexpr int kThreads = 128;
-constexpr int kGroup = 8;   // videos per batch group
-constexpr int kUnits = 8;   // hidden units per CTA
-constexpr long long kTimeoutCycles = 3000000000LL;  // ~1.5 s at 2 GHz
-
-constexpr uint32_t kStatusPollTimeout = 1;
-
-struct FwdParams {
-    const float* xproj;   // [B,T,4H]
-    const float* w_hh;    // [4H,H]
-    float* hs;            // [B,T,H]
-    float* gates;         // [B,T,4H] or null
-    float* cells;         // [B,T,H] or null
-    uint32_t* ring;       // [n_groups_total][2][8][H]   flagged copies of h_t
-    unsigned int* status; // 4 words
-    int B, T;
-    int group_offset;  // first batch group handled by this launch
-    int n_slices;      // H / 8
-};
-
-struct BwdParams {
-    const float* w_hh;    // [4H,H]
-    const float* gates;   // [B,T,4H]
-    const float* cells;   // [B,T,H]
-    const float* dh_out;  // [B,T,H]
-    float* dgates;        // [B,T,4H]
-    uint32_t* ring;       // [n_groups_total][2][H/U producers][8][H]  flagged partial products
-    unsigned int* status;
-    int B, T;
-    int group_offset;
-    int n_slices;
-};
-
-// parity carried by the words of step t: slot t&1 is rewritten every 2 steps, so the bit
-// alternates per rewrite; the first write (t = 0, 1) carries 1 to differ from the zeroed ring.
-__device__ __forceinline__ uint32_t step_parity(int t) { return ((uint32_t)(t >> 1) & 1u) ^ 1u; }
-
-__device__ __forceinline__ void st_flagged(uint32_t* p, float v, uint32_t parity) {
-    const uint32_t bits = (__float_as_uint(v) & ~1u) | parity;
-    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(bits) : "memory");
-}
-__device__ __forceinline__ uint4 ld_flagged4(const uint32_t* p) {
-    uint4 v;
-    // ld.volatile streams at ~80 B/clk/SM from L2, ld.relaxed.gpu / ld.global.cg at ~40 and ld.acquire.gpu at ~3
-    // (measured with tools/load_flavors.cu, profiles/r01_lstm_handoff.md); every 32-bit element is still a
-    // single-copy-atomic access that is always served by L2.
-    asm volatile("ld.volatile.global.v4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p)
-                 : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_flagged1(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.volatile.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ bool ready4(const uint4& v, uint32_t parity) {
-    return ((((v.x ^ parity) | (v.y ^ parity) | (v.z ^ parity) | (v.w ^ parity)) & 1u) == 0u);
-}
-
-// Time-out bookkeeping of the polling loops: called every 64 unsuccessful sweeps.  Returns true
-// when the caller must give up (another CTA reported a failure, or this wait has expired).
-__device__ __noinline__ bool poll_expired(long long t0, unsigned int* status, int t) {
-    if (ld_relaxed(status) != 0) return true;
-    if (clock64() - t0 > kTimeoutCycles) {
-        if (atomicCAS(status, 0u, kStatusPollTimeout) == 0u) {
-            status[1] = (unsigned int)t;
-            status[2] = blockIdx.x;
-            status[3] = threadIdx.x;
-        }
-        return true;
-    }
-    return false;
-}
-
-__device__ __forceinline__ uint4 ld_word(const uint4*, const uint32_t* p) { return ld_flagged4(p); }
-__device__ __forceinline__ uint32_t ld_word(const uint32_t*, const uint32_t* p) { return ld_flagged1(p); }
-__device__ __forceinline__ bool word_ready(const uint4& v, uint32_t parity) { return ready4(v, parity); }
-__device__ __forceinline__ bool word_ready(const uint32_t& v, uint32_t parity) { return (v & 1u) == parity; }
-
-// Fetch N flagged words (uint4 or uint32_t) whose addresses / validity are given by functors.
-// Every load of a sweep is issued back to back (one L2 round trip when the data is already there);
-// stale words are re-fetched in further sweeps.  (A variant that spun on a single canary word per
-// thread and fetched the rest afterwards was measured slower on B200 -- 10.0 vs 3.8 us/step for the
-// H=256 backward recurrence -- and was dropped; see profiles/r01_lstm_handoff.md.)
-// Returns false on time-out / abort.
-template <int N, typename Word, typename AddrFn, typename ValidFn>
-__device__ __forceinline__ bool gather_flagged(Word (&v)[N], AddrFn addr, ValidFn valid, uint32_t par,
-                                               unsigned int* status, int t) {
-    bool pending = false;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (valid(i)) v[i] = ld_word((const Word*)nullptr, addr(i));
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (valid(i) && !word_ready(v[i], par)) pending = true;
-    if (!pending) return true;
-
-    const long long t0 = clock64();
-    unsigned int sweeps = 0;
-    for (;;) {
-        pending = false;
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            if (valid(i) && !word_ready(v[i], par)) v[i] = ld_word((const Word*)nullptr, addr(i));
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            if (valid(i) && !word_ready(v[i], par)) pending = true;
-        if (!pending) return true;
-        if ((++sweeps & 63u) == 0 && poll_expired(t0, status, t)) return false;
-    }
-}
 
 template <int KPT, int NS>
 __device__ __forceinline__ void load_weight_row(float (&w)[KPT], const float* __restrict__ row, int ks) {
@@ -166,19 +52,19 @@ __device__ __forceinline__ void load_weight_row(float (&w)[KPT], const float* __
     }
 }
 
-// acc[rr*8 + b] += sum_e w[rr][e] * v(b, e) where, for KPT >= 4, the thread's operand vector
-// (b, j) is the float4 at v_s[(j*8 + b) * stride_vec + lane_vec]; for KPT < 4 the scalar (b, e)
-// is at v_s[(e*8 + b) * stride_vec + lane_vec].
+// acc[rr*8 + b] += sum_e w[rr][e] * v(b, k(e)) for the operand tile v_s = [8 videos][H] (row-major) in shared
+// memory.  Lane ks owns k = 4*ks + 128*j + i (KPT >= 4: one LDS.128 per (j, b), the warp reads 32 consecutive
+// 16-byte words) or k = ks + 32*e (KPT < 4).
 template <int KPT>
-__device__ __forceinline__ void matvec_tile(const float (&w)[kUnits][KPT], const float* v_s, int stride_vec,
-                                            int lane_vec, float (&acc)[64]) {
+__device__ __forceinline__ void matvec_tile(const float (&w)[kUnits][KPT], const float* v_s, int lane, float (&acc)[64]) {
+    constexpr int H = 32 * KPT;
     if (KPT >= 4) {
         const float4* v4 = reinterpret_cast<const float4*>(v_s);
 #pragma unroll
         for (int j = 0; j < KPT / 4; ++j) {
 #pragma unroll
             for (int b = 0; b < kGroup; ++b) {
-                const float4 hv = v4[(j * 8 + b) * stride_vec + lane_vec];
+                const float4 hv = v4[b * (H / 4) + j * 32 + lane];
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     float a = acc[rr * 8 + b];
@@ -195,7 +81,7 @@ __device__ __forceinline__ void matvec_tile(const float (&w)[kUnits][KPT], const
         for (int e = 0; e < KPT; ++e) {
 #pragma unroll
             for (int b = 0; b < kGroup; ++b) {
-                const float hv = v_s[(e * 8 + b) * stride_vec + lane_vec];
+                const float hv = v_s[b * H + e * 32 + lane];
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) acc[rr * 8 + b] = fmaf(w[rr][e], hv, acc[rr * 8 + b]);
             }
@@ -230,29 +116,35 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[64], int lane) 
 // ------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------
-// Shared-memory operand layout (both kernels): "vector slot" (j, b) of K-split ks lives at
-// float4 index (j*8 + b) * NS + ks, so a warp's LDS.128 touches 32 consecutive 16-byte words.
+// Shared-memory operand tile: h_{t-1} of the batch group as [8 videos][H], double buffered.
 // RG = row groups per CTA (128*RG threads, 8*RG hidden units).  RG = 2 is used at H = 512 so that a
 // batch of 32 videos is exactly one CTA per SM: two 128-thread CTAs per SM were measured to serialise
 // (5.2 us/step against 3.0 us/step with one), because they share the SM's L2 request path while polling.
-template <int KPT, int RG>
-__global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kernel(const FwdParams p) {
+//
+// CL = false: the exchange goes through the global-memory ring (any H, cooperative launch).
+// CL = true : the H/(8*RG) <= 16 CTAs of a batch group form one thread-block cluster; every CTA pushes its
+//             flagged h_t values directly into the operand tile of all CTAs of the cluster (DSMEM) and polls
+//             only its own shared memory -- no L2 round trip on the step path, no cooperative launch (clusters
+//             are co-scheduled by the hardware, batch groups are independent clusters).
+template <int KPT, int RG, bool CL>
+__global__ void __launch_bounds__(kThreads* RG, (RG == 1 && !CL) ? 2 : 1) lstm_fwd_kernel(const FwdParams p) {
     constexpr int H = 32 * KPT;
     constexpr int NT = kThreads * RG;
-    constexpr int VPR = (KPT >= 4) ? H / 4 : H;        // exchange words per video row (vectors or scalars)
-    constexpr int NV = (8 * VPR + NT - 1) / NT;        // per-thread loads per step
+    constexpr int U = kUnits * RG;
+    constexpr int CS = H / U;                          // CTAs per batch group (= cluster size when CL)
+    constexpr int NV = (8 * H / 4 + NT - 1) / NT;      // 16-byte vectors of the operand tile per thread
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* h_s = reinterpret_cast<float*>(smem_raw);  // [2][8*H]
+    float* h_s = reinterpret_cast<float*>(smem_raw);  // [2][8][H]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slice = blockIdx.x % p.n_slices;
     const int group = p.group_offset + blockIdx.x / p.n_slices;
-    const int u0 = slice * (kUnits * RG);
+    const int u0 = slice * U;
     const int b0 = group * kGroup;
     const int T = p.T;
     const int nvalid = min(kGroup, p.B - b0);
-    uint32_t* ring = p.ring + (size_t)group * (2 * kGroup * H);
+    uint32_t* ring = CL ? nullptr : p.ring + (size_t)group * (2 * kGroup * H);
 
     for (int i = tid; i < 2 * kGroup * H; i += NT) h_s[i] = 0.0f;
 
@@ -264,6 +156,7 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
         load_weight_row<KPT, 32>(w[rr], p.w_hh + (size_t)row * H, lane);
     }
     __syncthreads();
+    if (CL) cg::this_cluster().sync();  // every tile of the cluster is zeroed before the first remote store
 
     // after the butterfly this lane owns gates (2*gh, 2*gh+1) of cell (unit u, video bb)
     const int uu = lane >> 4, bl = (lane >> 1) & 7, gh = lane & 1;
@@ -287,40 +180,28 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
         for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
 
         if (t > 0) {
-            // ---- gather h_{t-1} of this batch group: flagged words -> shared memory -------------
+            // ---- h_{t-1} of this batch group: wait until every word of the tile carries the step parity ----
             const uint32_t par = step_parity(t - 1);
-            const uint32_t* src = ring + (size_t)((t - 1) & 1) * (kGroup * H);
             float* dst = h_s + ((t - 1) & 1) * (kGroup * H);
-            if (KPT >= 4) {
-                // vector idx = tid + 128*i: video b = idx / VPR, column col = idx % VPR (k = 4*col .. 4*col+3)
-                uint4 v[NV];
-                if (!gather_flagged(v, [&](int i) { return src + (size_t)(tid + NT * i) * 4; },
-                                    [&](int i) { return (tid + NT * i) / VPR < nvalid; }, par, p.status, t))
+            // vector idx = tid + NT*i covers video idx / (H/4), columns 4*(idx % (H/4)) ..
+            auto vec_valid = [&](int i) { return (tid + NT * i) < 8 * H / 4 && (tid + NT * i) / (H / 4) < nvalid; };
+            uint4 v[NV];
+            if (CL) {
+                const uint32_t tile = smem_u32(dst);
+                if (!gather_flagged(v, [&](int i) { return tile + (uint32_t)(tid + NT * i) * 16u; }, vec_valid, par,
+                                    p.status, t))
                     my_abort = 1;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    const int idx = tid + NT * i;
-                    const int b = idx / VPR, col = idx % VPR;
-                    // k = 4*ks + 128*j  ->  ks = col % 32, j = col / 32
-                    if (b < nvalid) reinterpret_cast<uint4*>(dst)[((col >> 5) * 8 + b) * 32 + (col & 31)] = v[i];
-                }
             } else {
-                // scalar idx = tid + 128*i: video b = idx / H, k = idx % H = ks + 32*e
-                uint32_t v[NV];
-                if (!gather_flagged(v, [&](int i) { return src + tid + NT * i; },
-                                    [&](int i) { return (tid + NT * i) < 8 * VPR && (tid + NT * i) / VPR < nvalid; },
-                                    par, p.status, t))
+                const uint32_t* src = ring + (size_t)((t - 1) & 1) * (kGroup * H);
+                if (!gather_flagged(v, [&](int i) { return src + (size_t)(tid + NT * i) * 4; }, vec_valid, par,
+                                    p.status, t))
                     my_abort = 1;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    const int idx = tid + NT * i;
-                    const int b = idx / VPR, k = idx % VPR;
-                    if (idx < 8 * VPR && b < nvalid)
-                        reinterpret_cast<uint32_t*>(dst)[((k >> 5) * 8 + b) * 32 + (k & 31)] = v[i];
-                }
+                for (int i = 0; i < NV; ++i)
+                    if (vec_valid(i)) reinterpret_cast<uint4*>(dst)[tid + NT * i] = v[i];
             }
             if (__syncthreads_or(my_abort)) break;
-            matvec_tile<KPT>(w, dst, 32, lane, acc);
+            matvec_tile<KPT>(w, dst, lane, acc);
             warp_transpose_reduce(acc, lane);
         }
 
@@ -337,9 +218,28 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
         const float go = gh ? act1 : oth1;
         c_state = fmaf(gf, c_state, gi * gg);
         const float hval = go * tanhf(c_state);
+        if (CL) {
+            // critical path first: push h_t of the warp's unit pair into the tile of every CTA of the cluster.
+            // All four lanes (uu, gh) of a video hold both values after one shuffle; each serves CS/4 peers with
+            // 8-byte stores.
+            const float other = __shfl_xor_sync(0xffffffffu, hval, 16);
+            if (valid && t + 1 < T) {
+                const uint32_t par = step_parity(t);
+                const uint32_t x = flagged(uu ? other : hval, par), y = flagged(uu ? hval : other, par);
+                const uint32_t local = smem_u32(h_s + (t & 1) * (kGroup * H) + bl * H + u0 + 2 * warp);
+                constexpr int PER = (CS >= 4) ? CS / 4 : 1;
+                const int q = uu * 2 + gh;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int d = q * PER + i;
+                    if (d < CS) st_peer_v2(map_to_cta(local, (uint32_t)d), x, y);
+                }
+            }
+        }
         if (valid) {
             // critical path first: publish h_t to the other CTAs of this batch group
-            if (gh == 0 && t + 1 < T) st_flagged(ring + (size_t)(t & 1) * (kGroup * H) + bl * H + u, hval, step_parity(t));
+            if (!CL && gh == 0 && t + 1 < T)
+                st_flagged(ring + (size_t)(t & 1) * (kGroup * H) + bl * H + u, hval, step_parity(t));
             const size_t row = row0 + t;
             if (gh == 0) {
                 p.hs[row * H + u] = hval;
@@ -360,6 +260,7 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
             }
         }
     }
+    if (CL) cg::this_cluster().sync();  // no CTA leaves while peers may still push into its shared memory
 }
 
 // ------------------------------------------------------------------------------------
@@ -380,8 +281,12 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_fwd_kern
 //      layout every warp load touched 32 different lines and H=256 ran at 4.05 us/step.
 // Per CTA and step 8*H*4 bytes are written and read (16 KB at H=512) against 8*4H*4 bytes read by the
 // gather formulation of the first version (64 KB, 6.05 us/step); no transposed copy of W_hh is needed.
-template <int KPT, int RG>
-__global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kernel(const BwdParams p) {
+//
+// CL = true: the NS <= 16 CTAs of a batch group form one thread-block cluster; producers push their partial sums
+// directly into the consumer's shared memory ([2][video][producer][unit], 8*H words per slot) and the consumer
+// polls its own shared memory.
+template <int KPT, int RG, bool CL>
+__global__ void __launch_bounds__(kThreads* RG, (RG == 1 && !CL) ? 2 : 1) lstm_bwd_kernel(const BwdParams p) {
     constexpr int H = 32 * KPT;
     constexpr int NT = kThreads * RG;
     constexpr int U = kUnits * RG;            // hidden units of this CTA
@@ -393,6 +298,7 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
     static_assert(NS <= 32 && 8 * VPC == 4 * (NT / 32), "4 gather vectors per thread");
 
     __shared__ __align__(16) float da_s[2][R][8];
+    __shared__ __align__(16) uint32_t rx_s[CL ? 2 * kGroup * H : 4];  // cluster flavour: inbox of partial sums
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slice = blockIdx.x % p.n_slices;
@@ -402,9 +308,11 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
     const int T = p.T;
     const int nvalid = min(kGroup, p.B - b0);
     constexpr size_t kSlotWords = (size_t)NS * kGroup * H;
-    uint32_t* ring = p.ring + (size_t)group * (2 * kSlotWords);
+    uint32_t* ring = CL ? nullptr : p.ring + (size_t)group * (2 * kSlotWords);
 
     for (int i = tid; i < 2 * R * 8; i += NT) (&da_s[0][0][0])[i] = 0.0f;  // rows of absent videos stay zero
+    if (CL)
+        for (int i = tid; i < 2 * kGroup * H; i += NT) rx_s[i] = 0u;
 
     // weights: local row r = gate*U + unit  ->  W_hh row gate*H + u0 + unit, columns KC*tid ..
     float w[R][KC];
@@ -456,6 +364,7 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
     };
     if (valid) load_stash(T - 1);
     __syncthreads();
+    if (CL) cg::this_cluster().sync();  // every inbox of the cluster is zeroed before the first remote store
 
     int my_abort = 0;
 
@@ -495,7 +404,7 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
 
         // ---- 2. partial[b][k] over the own rows; publish ------------------------------------------------
         const uint32_t par = step_parity(s);
-        uint32_t* slot = ring + (size_t)buf * kSlotWords;
+        uint32_t* slot = CL ? nullptr : ring + (size_t)buf * kSlotWords;
         if (tid < NACT) {
             float acc[8][KC];
 #pragma unroll
@@ -514,17 +423,32 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
             }
             // column k = KC*tid belongs to consumer k / U, unit k % U: word [consumer][b][producer = slice][unit]
             const int k0 = KC * tid;
-            uint32_t* out = slot + ((size_t)(k0 / U) * kGroup * NS + slice) * U + (k0 % U);
+            if (CL) {
+                const uint32_t inbox = map_to_cta(smem_u32(&rx_s[((size_t)buf * kGroup * NS + slice) * U + (k0 % U)]),
+                                                  (uint32_t)(k0 / U));
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (b < nvalid) {
-                    uint32_t* dst = out + (size_t)b * NS * U;
-                    if (KC == 2) {
-                        const uint32_t x = (__float_as_uint(acc[b][0]) & ~1u) | par;
-                        const uint32_t y = (__float_as_uint(acc[b][KC - 1]) & ~1u) | par;
-                        asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(x), "r"(y) : "memory");
-                    } else {
-                        st_flagged(dst, acc[b][0], par);
+                for (int b = 0; b < 8; ++b) {
+                    if (b < nvalid) {
+                        const uint32_t dst = inbox + (uint32_t)(b * NS * U) * 4u;
+                        if (KC == 2)
+                            st_peer_v2(dst, flagged(acc[b][0], par), flagged(acc[b][KC - 1], par));
+                        else
+                            st_peer_b32(dst, flagged(acc[b][0], par));
+                    }
+                }
+            } else {
+                uint32_t* out = slot + ((size_t)(k0 / U) * kGroup * NS + slice) * U + (k0 % U);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (b < nvalid) {
+                        uint32_t* dst = out + (size_t)b * NS * U;
+                        if (KC == 2) {
+                            const uint32_t x = (__float_as_uint(acc[b][0]) & ~1u) | par;
+                            const uint32_t y = (__float_as_uint(acc[b][KC - 1]) & ~1u) | par;
+                            asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(x), "r"(y) : "memory");
+                        } else {
+                            st_flagged(dst, acc[b][0], par);
+                        }
                     }
                 }
             }
@@ -533,16 +457,25 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
         // ---- 3. reduce-scatter: sum the producers' partials for the own units ---------------------------
         {
             // this CTA's block of the slot: [b][producer][U] words = per video NS*VPC uint4, contiguous
-            const uint32_t* src = slot + (size_t)slice * kGroup * NS * U;
             uint4 v[4];
             // load i of lane l:  RG=1: video 2w + (i>>1), vector (i&1)*32 + l  ->  producer vec/2, unit quad l&1
             //                    RG=2: video w,            vector i*32 + l      ->  producer vec/4, unit quad l&3
             auto vec_b = [&](int i) { return RG == 1 ? 2 * warp + (i >> 1) : warp; };
             auto vec_id = [&](int i) { return RG == 1 ? (i & 1) * 32 + lane : i * 32 + lane; };
-            if (!gather_flagged(
-                    v, [&](int i) { return src + ((size_t)vec_b(i) * NS * VPC + vec_id(i)) * 4; },
-                    [&](int i) { return vec_id(i) < NS * VPC && vec_b(i) < nvalid; }, par, p.status, t))
-                my_abort = 1;
+            auto vec_valid = [&](int i) { return vec_id(i) < NS * VPC && vec_b(i) < nvalid; };
+            if (CL) {
+                const uint32_t inbox = smem_u32(&rx_s[(size_t)buf * kGroup * H]);
+                if (!gather_flagged(
+                        v, [&](int i) { return inbox + (uint32_t)(vec_b(i) * NS * VPC + vec_id(i)) * 16u; }, vec_valid,
+                        par, p.status, t))
+                    my_abort = 1;
+            } else {
+                const uint32_t* src = slot + (size_t)slice * kGroup * NS * U;
+                if (!gather_flagged(
+                        v, [&](int i) { return src + ((size_t)vec_b(i) * NS * VPC + vec_id(i)) * 4; }, vec_valid, par,
+                        p.status, t))
+                    my_abort = 1;
+            }
             float f[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -577,6 +510,7 @@ __global__ void __launch_bounds__(kThreads* RG, (RG == 1) ? 2 : 1) lstm_bwd_kern
             }
         }
     }
+    if (CL) cg::this_cluster().sync();  // no CTA leaves while peers may still push into its inbox
 }
 
 // ---- host side ----------------------------------------------------------------------
@@ -617,7 +551,7 @@ int launch_fwd(FwdParams p, int64_t B, cudaStream_t stream) {
     constexpr int H = 32 * KPT;
     const size_t smem = (size_t)2 * kGroup * H * sizeof(float);
     int cap = 0;
-    int rc = max_coresident(lstm_fwd_kernel<KPT, RG>, kThreads * RG, smem, &cap);
+    int rc = max_coresident(lstm_fwd_kernel<KPT, RG, false>, kThreads * RG, smem, &cap);
     if (rc != OPN_OK) return rc;
     const int n_slices = H / (kUnits * RG);
     const int groups = (int)((B + kGroup - 1) / kGroup);
@@ -631,7 +565,7 @@ int launch_fwd(FwdParams p, int64_t B, cudaStream_t stream) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
         void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel<KPT, RG>, dim3(n_slices * ng),
+        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel<KPT, RG, false>, dim3(n_slices * ng),
                                              dim3(kThreads * RG), args, smem, stream));
         count_launch();
     }
@@ -643,7 +577,7 @@ int launch_bwd(BwdParams p, int64_t B, cudaStream_t stream) {
     constexpr int H = 32 * KPT;
     const size_t smem = 0;
     int cap = 0;
-    int rc = max_coresident(lstm_bwd_kernel<KPT, RG>, kThreads * RG, smem, &cap);
+    int rc = max_coresident(lstm_bwd_kernel<KPT, RG, false>, kThreads * RG, smem, &cap);
     if (rc != OPN_OK) return rc;
     const int n_slices = H / (kUnits * RG);
     const int groups = (int)((B + kGroup - 1) / kGroup);
@@ -657,11 +591,82 @@ int launch_bwd(BwdParams p, int64_t B, cudaStream_t stream) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
         void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KPT, RG>, dim3(n_slices * ng),
+        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KPT, RG, false>, dim3(n_slices * ng),
                                              dim3(kThreads * RG), args, smem, stream));
         count_launch();
     }
     return OPN_OK;
+}
+
+// Cluster flavour: one launch, one thread-block cluster of H/(8*RG) CTAs per batch group.  Clusters are
+// independent, so the grid may exceed the device (later clusters start as earlier ones retire).
+// *launched = false (and OPN_OK) when this device cannot host such a cluster: the caller falls back to the ring.
+template <typename Kernel, typename Params>
+int launch_cluster(Kernel kernel, Params p, int threads, int cluster_size, size_t smem, int64_t B, cudaStream_t stream,
+                   bool* launched) {
+    *launched = false;
+    if (cluster_size > 8)
+        OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int groups = (int)((B + kGroup - 1) / kGroup);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * cluster_size));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        (void)cudaGetLastError();
+        return OPN_OK;
+    }
+    p.n_slices = cluster_size;
+    p.group_offset = 0;
+    OPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+    count_launch();
+    *launched = true;
+    return OPN_OK;
+}
+
+// exchange medium of the FP32-FMA kernels: "cluster" (DSMEM, H <= 256) or "l2" (global-memory ring, any H; default:
+// with 8-byte peer stores the cluster flavour measured 2.86 us/step against 2.08 for the ring at H = 256 forward)
+bool want_cluster() {
+    const char* e = getenv("OPN_LSTM_EXCHANGE");
+    return e && e[0] == 'c';
+}
+
+template <int KPT, int RG>
+int run_fwd(const FwdParams& p, int64_t B, cudaStream_t s, bool cluster_ok) {
+    constexpr int H = 32 * KPT;
+    if constexpr (H / (kUnits * RG) <= 16) {
+        if (cluster_ok && want_cluster()) {
+            bool launched = false;
+            const int rc = launch_cluster(lstm_fwd_kernel<KPT, RG, true>, p, kThreads * RG, H / (kUnits * RG),
+                                          (size_t)2 * kGroup * H * sizeof(float), B, s, &launched);
+            if (rc != OPN_OK || launched) return rc;
+        }
+    }
+    return launch_fwd<KPT, RG>(p, B, s);
+}
+
+template <int KPT, int RG>
+int run_bwd(const BwdParams& p, int64_t B, cudaStream_t s, bool cluster_ok) {
+    constexpr int H = 32 * KPT;
+    if constexpr (H / (kUnits * RG) <= 16) {
+        if (cluster_ok && want_cluster()) {
+            bool launched = false;
+            const int rc = launch_cluster(lstm_bwd_kernel<KPT, RG, true>, p, kThreads * RG, H / (kUnits * RG), 0, B, s,
+                                          &launched);
+            if (rc != OPN_OK || launched) return rc;
+        }
+    }
+    return launch_bwd<KPT, RG>(p, B, s);
 }
 
 }  // namespace
@@ -701,16 +706,13 @@ extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj,
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
+    // cluster size = H / units per CTA must be <= 16: 8-unit CTAs up to H = 128, 16-unit CTAs at H = 256
     switch (H) {
-        case 32: return launch_fwd<1, 1>(p, B, s);
-        case 64: return launch_fwd<2, 1>(p, B, s);
-        case 128: return launch_fwd<4, 1>(p, B, s);
-        case 256: return launch_fwd<8, 1>(p, B, s);
-        default: {
-            const char* e = getenv("OPN_LSTM_FWD_RG");
-            if (e && e[0] == '1') return launch_fwd<16, 1>(p, B, s);
-            return launch_fwd<16, 2>(p, B, s);
-        }
+        case 32: return run_fwd<1, 1>(p, B, s, true);
+        case 64: return run_fwd<2, 1>(p, B, s, true);
+        case 128: return run_fwd<4, 1>(p, B, s, true);
+        case 256: return want_cluster() ? run_fwd<8, 2>(p, B, s, true) : run_fwd<8, 1>(p, B, s, false);
+        default: return run_fwd<16, 2>(p, B, s, false);
     }
 }
 
@@ -742,11 +744,11 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     p.group_offset = 0;
     p.n_slices = 0;
     switch (H) {
-        case 32: return launch_bwd<1, 1>(p, B, s);
-        case 64: return launch_bwd<2, 1>(p, B, s);
-        case 128: return launch_bwd<4, 1>(p, B, s);
-        case 256: return launch_bwd<8, 1>(p, B, s);
-        default: return launch_bwd<16, 2>(p, B, s);
+        case 32: return run_bwd<1, 1>(p, B, s, true);
+        case 64: return run_bwd<2, 1>(p, B, s, true);
+        case 128: return run_bwd<4, 1>(p, B, s, true);
+        case 256: return want_cluster() ? run_bwd<8, 2>(p, B, s, true) : run_bwd<8, 1>(p, B, s, false);
+        default: return run_bwd<16, 2>(p, B, s, false);
     }
 }
 

@@ -1,0 +1,147 @@
+// Shared pieces of the persistent LSTM recurrence kernels (opn_lstm.cu: FP32 FMA math; opn_lstm_mma.cu:
+// split-fp16 tensor-core math): launch parameters, the flag-in-data exchange primitives for both media
+// (global-memory ring / thread-block-cluster shared memory), the polling gather with its time-out.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "opn_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace opn {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kGroup = 8;   // videos per batch group
+constexpr int kUnits = 8;   // hidden units per CTA
+constexpr long long kTimeoutCycles = 3000000000LL;  // ~1.5 s at 2 GHz
+
+constexpr uint32_t kStatusPollTimeout = 1;
+
+struct FwdParams {
+    const float* xproj;   // [B,T,4H]
+    const float* w_hh;    // [4H,H]
+    float* hs;            // [B,T,H]
+    float* gates;         // [B,T,4H] or null
+    float* cells;         // [B,T,H] or null
+    uint32_t* ring;       // [n_groups_total][2][8][H]   flagged copies of h_t
+    unsigned int* status; // 4 words
+    int B, T;
+    int group_offset;  // first batch group handled by this launch
+    int n_slices;      // H / 8
+};
+
+struct BwdParams {
+    const float* w_hh;    // [4H,H]
+    const float* gates;   // [B,T,4H]
+    const float* cells;   // [B,T,H]
+    const float* dh_out;  // [B,T,H]
+    float* dgates;        // [B,T,4H]
+    uint32_t* ring;       // [n_groups_total][2][H/U producers][8][H]  flagged partial products
+    unsigned int* status;
+    int B, T;
+    int group_offset;
+    int n_slices;
+};
+
+// parity carried by the words of step t: slot t&1 is rewritten every 2 steps, so the bit
+// alternates per rewrite; the first write (t = 0, 1) carries 1 to differ from the zeroed ring.
+__device__ __forceinline__ uint32_t step_parity(int t) { return ((uint32_t)(t >> 1) & 1u) ^ 1u; }
+
+__device__ __forceinline__ void st_flagged(uint32_t* p, float v, uint32_t parity) {
+    const uint32_t bits = (__float_as_uint(v) & ~1u) | parity;
+    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(bits) : "memory");
+}
+__device__ __forceinline__ uint4 ld_flagged4(const uint32_t* p) {
+    uint4 v;
+    // ld.volatile streams at ~80 B/clk/SM from L2, ld.relaxed.gpu / ld.global.cg at ~40 and ld.acquire.gpu at ~3
+    // (measured with tools/load_flavors.cu, profiles/r01_lstm_handoff.md); every 32-bit element is still a
+    // single-copy-atomic access that is always served by L2.
+    asm volatile("ld.volatile.global.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ bool ready4(const uint4& v, uint32_t parity) {
+    return ((((v.x ^ parity) | (v.y ^ parity) | (v.z ^ parity) | (v.w ^ parity)) & 1u) == 0u);
+}
+
+// Time-out bookkeeping of the polling loops: called every 64 unsuccessful sweeps.  Returns true
+// when the caller must give up (another CTA reported a failure, or this wait has expired).
+__device__ __noinline__ bool poll_expired(long long t0, unsigned int* status, int t) {
+    if (ld_relaxed(status) != 0) return true;
+    if (clock64() - t0 > kTimeoutCycles) {
+        if (atomicCAS(status, 0u, kStatusPollTimeout) == 0u) {
+            status[1] = (unsigned int)t;
+            status[2] = blockIdx.x;
+            status[3] = threadIdx.x;
+        }
+        return true;
+    }
+    return false;
+}
+
+// ---- thread-block-cluster flavour of the exchange: peers push flagged words straight into this CTA's shared
+// memory (st.shared::cluster through a mapa-translated address) and the CTA polls its OWN shared memory.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_peer_v2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.relaxed.cluster.shared::cluster.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void st_peer_b32(uint32_t a, uint32_t x) {
+    asm volatile("st.relaxed.cluster.shared::cluster.b32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+}
+__device__ __forceinline__ uint4 lds_flagged4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(a)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t flagged(float v, uint32_t parity) { return (__float_as_uint(v) & ~1u) | parity; }
+
+__device__ __forceinline__ uint4 ld_word(const uint4*, const uint32_t* p) { return ld_flagged4(p); }
+__device__ __forceinline__ uint4 ld_word(const uint4*, uint32_t smem_addr) { return lds_flagged4(smem_addr); }
+__device__ __forceinline__ bool word_ready(const uint4& v, uint32_t parity) { return ready4(v, parity); }
+
+// Fetch N flagged words (uint4 or uint32_t) whose addresses / validity are given by functors.
+// Every load of a sweep is issued back to back (one L2 round trip when the data is already there);
+// stale words are re-fetched in further sweeps.  (A variant that spun on a single canary word per
+// thread and fetched the rest afterwards was measured slower on B200 -- 10.0 vs 3.8 us/step for the
+// H=256 backward recurrence -- and was dropped; see profiles/r01_lstm_handoff.md.)
+// Returns false on time-out / abort.
+template <int N, typename Word, typename AddrFn, typename ValidFn>
+__device__ __forceinline__ bool gather_flagged(Word (&v)[N], AddrFn addr, ValidFn valid, uint32_t par,
+                                               unsigned int* status, int t) {
+    bool pending = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (valid(i)) v[i] = ld_word((const Word*)nullptr, addr(i));
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (valid(i) && !word_ready(v[i], par)) pending = true;
+    if (!pending) return true;
+
+    const long long t0 = clock64();
+    unsigned int sweeps = 0;
+    for (;;) {
+        pending = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (valid(i) && !word_ready(v[i], par)) v[i] = ld_word((const Word*)nullptr, addr(i));
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (valid(i) && !word_ready(v[i], par)) pending = true;
+        if (!pending) return true;
+        if ((++sweeps & 63u) == 0 && poll_expired(t0, status, t)) return false;
+    }
+}
+
+}  // namespace
+}  // namespace opn

@@ -112,9 +112,14 @@ def _lstm_case(B, T, I, H, seed, scale=1.0):
     return x, w_ih, w_hh, dh
 
 
+# the two exchange media of the recurrence: thread-block cluster + DSMEM (H <= 256) and the global-memory ring
+@pytest.mark.parametrize("exchange", ["cluster", "l2"])
 @pytest.mark.parametrize("H", [32, 64, 128, 256, 512])
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 8), (8, 5), (11, 17), (32, 12)])
-def test_lstm_layer_forward_backward(cuda_device, H, B, T):
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 8), (8, 5), (11, 17), (32, 12), (70, 9)])
+def test_lstm_layer_forward_backward(cuda_device, monkeypatch, exchange, H, B, T):
+    if H == 512 and exchange == "cluster":
+        pytest.skip("H=512 has no cluster flavour (32 CTAs per batch group)")
+    monkeypatch.setenv("OPN_LSTM_EXCHANGE", exchange)
     I = 6 if H != 64 else 75
     x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=100 * H + B + T)
     xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
@@ -131,7 +136,9 @@ def test_lstm_layer_forward_backward(cuda_device, H, B, T):
         assert err <= 5e-5 * scale, (name, err, scale)
 
 
-def test_lstm_saturating_weights(cuda_device):
+@pytest.mark.parametrize("exchange", ["cluster", "l2"])
+def test_lstm_saturating_weights(cuda_device, monkeypatch, exchange):
+    monkeypatch.setenv("OPN_LSTM_EXCHANGE", exchange)
     B, T, I, H = 9, 40, 90, 256
     x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=7, scale=8.0)
     xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
@@ -143,6 +150,27 @@ def test_lstm_saturating_weights(cuda_device):
     assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-4
     for got, want in ((xg.grad, xr.grad), (wig.grad, wir.grad), (whg.grad, whr.grad)):
         assert (got.cpu().double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("exchange", ["cluster", "l2"])
+@pytest.mark.parametrize("H,T", [(256, 300), (128, 120)])
+def test_lstm_long_sequence_both_exchanges(cuda_device, monkeypatch, exchange, H, T):
+    """T = 300 at the OPNet LSTM1 shape: 299 exchanges per launch, every ring / inbox slot reused ~150 times."""
+    monkeypatch.setenv("OPN_LSTM_EXCHANGE", exchange)
+    B, I = 32, 90
+    x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=31)
+    dh = dh * 0.01
+    xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
+    ref = oracle.lstm_layer(xr, wir, whr)
+    ref.backward(dh.double())
+    xg, wig, whg = [t.to(cuda_device).requires_grad_(True) for t in (x, w_ih, w_hh)]
+    out = ops.lstm_layer(xg, wig, whg)
+    out.backward(dh.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5
+    for name, got, want in (("dx", xg.grad, xr.grad), ("dw_ih", wig.grad, wir.grad), ("dw_hh", whg.grad, whr.grad)):
+        scale = max(1.0, want.abs().max().item())
+        err = (got.cpu().double() - want).abs().max().item()
+        assert err <= 1e-4 * scale, (name, err, scale)
 
 
 def test_lstm_inference_mode_skips_stash(cuda_device):

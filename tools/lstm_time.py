@@ -7,7 +7,9 @@ from ctypes import c_uint32
 lib = _lib.load(); dev = torch.device("cuda:0")
 T = 300
 import itertools
-for B, H in itertools.product([int(x) for x in os.environ.get("BS", "32").split(",")], (256, 512)):
+HS = [int(x) for x in os.environ.get("HS", "256,512").split(",")]
+print("exchange =", os.environ.get("OPN_LSTM_EXCHANGE", "(default)"))
+for B, H in itertools.product([int(x) for x in os.environ.get("BS", "32").split(",")], HS):
     xp = torch.randn(B, T, 4 * H, device=dev) * 0.5
     whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / (H ** 0.5)
     hs = torch.empty(B, T, H, device=dev); gates = torch.empty(B, T, 4 * H, device=dev); cells = torch.empty(B, T, H, device=dev)
