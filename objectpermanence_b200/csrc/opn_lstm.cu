@@ -89,20 +89,6 @@ __device__ __forceinline__ void matvec_tile(const float (&w)[kUnits][KPT], const
     }
 }
 
-// One stage of the transposing butterfly: the N live values (compact index) are halved; bit
-// ABIT of the compact index is resolved by lane bit `mask`.
-template <int N, int ABIT, int SZ>
-__device__ __forceinline__ void butterfly_stage(float (&v)[SZ], bool hi, int mask) {
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        const int lo = ((i >> ABIT) << (ABIT + 1)) | (i & ((1 << ABIT) - 1));
-        const int up = lo | (1 << ABIT);
-        const float send = hi ? v[lo] : v[up];
-        const float keep = hi ? v[up] : v[lo];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-    }
-}
-
 // Sum acc[64] over the 32 lanes of the warp.  On return lane l holds in v[0], v[1] the totals
 // of index  a = ((l>>4)&1)<<5 | (l&1)<<4 | j<<3 | ((l>>1)&7)   for j = 0, 1.
 __device__ __forceinline__ void warp_transpose_reduce(float (&v)[64], int lane) {
@@ -535,105 +521,6 @@ WorkspaceLayout layout(int64_t B, int64_t T, int64_t H) {
 
 bool supported_hidden(int64_t H) { return H == 32 || H == 64 || H == 128 || H == 256 || H == 512; }
 
-template <typename Kernel>
-int max_coresident(Kernel kernel, int threads, size_t smem, int* out) {
-    int dev = 0, sms = 0, per_sm = 0;
-    OPN_CUDA(cudaGetDevice(&dev));
-    OPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    *out = sms * per_sm;
-    return OPN_OK;
-}
-
-template <int KPT, int RG>
-int launch_fwd(FwdParams p, int64_t B, cudaStream_t stream) {
-    constexpr int H = 32 * KPT;
-    const size_t smem = (size_t)2 * kGroup * H * sizeof(float);
-    int cap = 0;
-    int rc = max_coresident(lstm_fwd_kernel<KPT, RG, false>, kThreads * RG, smem, &cap);
-    if (rc != OPN_OK) return rc;
-    const int n_slices = H / (kUnits * RG);
-    const int groups = (int)((B + kGroup - 1) / kGroup);
-    const int per_launch = cap / n_slices;
-    if (per_launch < 1) {
-        set_error("lstm_fwd: device cannot co-schedule %d CTAs (capacity %d)", n_slices, cap);
-        return OPN_ERR_UNSUPPORTED;
-    }
-    p.n_slices = n_slices;
-    for (int g0 = 0; g0 < groups; g0 += per_launch) {
-        const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
-        p.group_offset = g0;
-        void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_fwd_kernel<KPT, RG, false>, dim3(n_slices * ng),
-                                             dim3(kThreads * RG), args, smem, stream));
-        count_launch();
-    }
-    return OPN_OK;
-}
-
-template <int KPT, int RG>
-int launch_bwd(BwdParams p, int64_t B, cudaStream_t stream) {
-    constexpr int H = 32 * KPT;
-    const size_t smem = 0;
-    int cap = 0;
-    int rc = max_coresident(lstm_bwd_kernel<KPT, RG, false>, kThreads * RG, smem, &cap);
-    if (rc != OPN_OK) return rc;
-    const int n_slices = H / (kUnits * RG);
-    const int groups = (int)((B + kGroup - 1) / kGroup);
-    const int per_launch = cap / n_slices;
-    if (per_launch < 1) {
-        set_error("lstm_bwd: device cannot co-schedule %d CTAs (capacity %d)", n_slices, cap);
-        return OPN_ERR_UNSUPPORTED;
-    }
-    p.n_slices = n_slices;
-    for (int g0 = 0; g0 < groups; g0 += per_launch) {
-        const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
-        p.group_offset = g0;
-        void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_kernel<KPT, RG, false>, dim3(n_slices * ng),
-                                             dim3(kThreads * RG), args, smem, stream));
-        count_launch();
-    }
-    return OPN_OK;
-}
-
-// Cluster flavour: one launch, one thread-block cluster of H/(8*RG) CTAs per batch group.  Clusters are
-// independent, so the grid may exceed the device (later clusters start as earlier ones retire).
-// *launched = false (and OPN_OK) when this device cannot host such a cluster: the caller falls back to the ring.
-template <typename Kernel, typename Params>
-int launch_cluster(Kernel kernel, Params p, int threads, int cluster_size, size_t smem, int64_t B, cudaStream_t stream,
-                   bool* launched) {
-    *launched = false;
-    if (cluster_size > 8)
-        OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int groups = (int)((B + kGroup - 1) / kGroup);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(groups * cluster_size));
-    cfg.blockDim = dim3((unsigned)threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster_size;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters < 1) {
-        (void)cudaGetLastError();
-        return OPN_OK;
-    }
-    p.n_slices = cluster_size;
-    p.group_offset = 0;
-    OPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
-    count_launch();
-    *launched = true;
-    return OPN_OK;
-}
-
 // exchange medium of the FP32-FMA kernels: "cluster" (DSMEM, H <= 256) or "l2" (global-memory ring, any H; default:
 // with 8-byte peer stores the cluster flavour measured 2.86 us/step against 2.08 for the ring at H = 256 forward)
 bool want_cluster() {
@@ -652,7 +539,8 @@ int run_fwd(const FwdParams& p, int64_t B, cudaStream_t s, bool cluster_ok) {
             if (rc != OPN_OK || launched) return rc;
         }
     }
-    return launch_fwd<KPT, RG>(p, B, s);
+    return launch_ring(lstm_fwd_kernel<KPT, RG, false>, p, kThreads * RG, H / (kUnits * RG),
+                       (size_t)2 * kGroup * H * sizeof(float), B, s, "lstm_fwd");
 }
 
 template <int KPT, int RG>
@@ -666,13 +554,28 @@ int run_bwd(const BwdParams& p, int64_t B, cudaStream_t s, bool cluster_ok) {
             if (rc != OPN_OK || launched) return rc;
         }
     }
-    return launch_bwd<KPT, RG>(p, B, s);
+    return launch_ring(lstm_bwd_kernel<KPT, RG, false>, p, kThreads * RG, H / (kUnits * RG), 0, B, s, "lstm_bwd");
 }
 
 }  // namespace
 }  // namespace opn
 
+namespace opn {
+// tensor-core flavour of the recurrence (opn_lstm_mma.cu)
+bool lstm_mma_supported(int64_t H);
+int lstm_fwd_mma(const FwdParams& p, int64_t B, int64_t H, cudaStream_t s);
+int lstm_bwd_mma(const BwdParams& p, int64_t B, int64_t H, cudaStream_t s);
+}  // namespace opn
+
 using namespace opn;
+
+// per-step matvec engine: split-fp16 tensor-core MMAs where they exist (H = 256, 512), FP32 FMA otherwise or when
+// OPN_LSTM_MATH=ffma asks for it
+static bool want_mma(int64_t H) {
+    const char* e = getenv("OPN_LSTM_MATH");
+    if (e && e[0] == 'f') return false;
+    return lstm_mma_supported(H);
+}
 
 extern "C" int64_t opn_lstm_workspace_bytes(int64_t B, int64_t T, int64_t H) {
     if (B <= 0 || T <= 0 || H <= 0) return 0;
@@ -706,6 +609,7 @@ extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj,
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
+    if (want_mma(H)) return lstm_fwd_mma(p, B, H, s);
     // cluster size = H / units per CTA must be <= 16: 8-unit CTAs up to H = 128, 16-unit CTAs at H = 256
     switch (H) {
         case 32: return run_fwd<1, 1>(p, B, s, true);
@@ -743,6 +647,7 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 0;
+    if (want_mma(H)) return lstm_bwd_mma(p, B, H, s);
     switch (H) {
         case 32: return run_bwd<1, 1>(p, B, s, true);
         case 64: return run_bwd<2, 1>(p, B, s, true);

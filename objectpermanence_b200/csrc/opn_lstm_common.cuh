@@ -10,8 +10,6 @@ namespace cg = cooperative_groups;
 
 namespace opn {
 
-namespace {
-
 constexpr int kThreads = 128;
 constexpr int kGroup = 8;   // videos per batch group
 constexpr int kUnits = 8;   // hidden units per CTA
@@ -44,6 +42,8 @@ struct BwdParams {
     int group_offset;
     int n_slices;
 };
+
+namespace {
 
 // parity carried by the words of step t: slot t&1 is rewritten every 2 steps, so the bit
 // alternates per rewrite; the first write (t = 0, 1) carries 1 to differ from the zeroed ring.
@@ -141,6 +141,94 @@ __device__ __forceinline__ bool gather_flagged(Word (&v)[N], AddrFn addr, ValidF
         if (!pending) return true;
         if ((++sweeps & 63u) == 0 && poll_expired(t0, status, t)) return false;
     }
+}
+
+// One stage of the transposing butterfly: the N live values (compact index) are halved; bit
+// ABIT of the compact index is resolved by lane bit `mask`.
+template <int N, int ABIT, int SZ>
+__device__ __forceinline__ void butterfly_stage(float (&v)[SZ], bool hi, int mask) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const int lo = ((i >> ABIT) << (ABIT + 1)) | (i & ((1 << ABIT) - 1));
+        const int up = lo | (1 << ABIT);
+        const float send = hi ? v[lo] : v[up];
+        const float keep = hi ? v[up] : v[lo];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+}
+
+// ---- host-side launch helpers ---------------------------------------------------------------------------
+template <typename Kernel>
+int max_coresident(Kernel kernel, int threads, size_t smem, int* out) {
+    int dev = 0, sms = 0, per_sm = 0;
+    OPN_CUDA(cudaGetDevice(&dev));
+    OPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    *out = sms * per_sm;
+    return OPN_OK;
+}
+
+// Ring flavour: the n_slices CTAs of a batch group exchange through global memory, so they must be co-resident:
+// cooperative launches of as many whole batch groups as fit on the device.
+template <typename Kernel, typename Params>
+int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem, int64_t B, cudaStream_t stream,
+                const char* what) {
+    int cap = 0;
+    int rc = max_coresident(kernel, threads, smem, &cap);
+    if (rc != OPN_OK) return rc;
+    const int groups = (int)((B + kGroup - 1) / kGroup);
+    const int per_launch = cap / n_slices;
+    if (per_launch < 1) {
+        set_error("%s: device cannot co-schedule %d CTAs (capacity %d)", what, n_slices, cap);
+        return OPN_ERR_UNSUPPORTED;
+    }
+    p.n_slices = n_slices;
+    for (int g0 = 0; g0 < groups; g0 += per_launch) {
+        const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
+        p.group_offset = g0;
+        void* args[] = {(void*)&p};
+        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(n_slices * ng), dim3(threads), args, smem,
+                                             stream));
+        count_launch();
+    }
+    return OPN_OK;
+}
+
+// Cluster flavour: one launch, one thread-block cluster of `cluster_size` CTAs per batch group.  Clusters are
+// independent, so the grid may exceed the device (later clusters start as earlier ones retire).
+// *launched = false (and OPN_OK) when this device cannot host such a cluster: the caller falls back to the ring.
+template <typename Kernel, typename Params>
+int launch_cluster(Kernel kernel, Params p, int threads, int cluster_size, size_t smem, int64_t B, cudaStream_t stream,
+                   bool* launched) {
+    *launched = false;
+    if (cluster_size > 8)
+        OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int groups = (int)((B + kGroup - 1) / kGroup);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * cluster_size));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        (void)cudaGetLastError();
+        return OPN_OK;
+    }
+    p.n_slices = cluster_size;
+    p.group_offset = 0;
+    OPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+    count_launch();
+    *launched = true;
+    return OPN_OK;
 }
 
 }  // namespace

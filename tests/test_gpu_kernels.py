@@ -112,14 +112,25 @@ def _lstm_case(B, T, I, H, seed, scale=1.0):
     return x, w_ih, w_hh, dh
 
 
-# the two exchange media of the recurrence: thread-block cluster + DSMEM (H <= 256) and the global-memory ring
-@pytest.mark.parametrize("exchange", ["cluster", "l2"])
+# flavours of the recurrence kernels: matvec on the tensor cores (split fp16, H = 256 / 512) or FP32 FMA; the FMA
+# kernels exchange through the global-memory ring or, for H <= 256, through a thread-block cluster (DSMEM)
+LSTM_FLAVOURS = ["mma", "ffma-l2", "ffma-cluster"]
+
+
+def _set_lstm_flavour(monkeypatch, flavour, H):
+    if flavour == "mma" and H not in (256, 512):
+        pytest.skip("tensor-core recurrence exists for H = 256, 512")
+    if flavour == "ffma-cluster" and H == 512:
+        pytest.skip("H=512 has no cluster flavour (32 CTAs per batch group)")
+    monkeypatch.setenv("OPN_LSTM_MATH", "mma" if flavour == "mma" else "ffma")
+    monkeypatch.setenv("OPN_LSTM_EXCHANGE", "cluster" if flavour == "ffma-cluster" else "l2")
+
+
+@pytest.mark.parametrize("flavour", LSTM_FLAVOURS)
 @pytest.mark.parametrize("H", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("B,T", [(1, 1), (2, 8), (8, 5), (11, 17), (32, 12), (70, 9)])
-def test_lstm_layer_forward_backward(cuda_device, monkeypatch, exchange, H, B, T):
-    if H == 512 and exchange == "cluster":
-        pytest.skip("H=512 has no cluster flavour (32 CTAs per batch group)")
-    monkeypatch.setenv("OPN_LSTM_EXCHANGE", exchange)
+def test_lstm_layer_forward_backward(cuda_device, monkeypatch, flavour, H, B, T):
+    _set_lstm_flavour(monkeypatch, flavour, H)
     I = 6 if H != 64 else 75
     x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=100 * H + B + T)
     xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
@@ -136,10 +147,11 @@ def test_lstm_layer_forward_backward(cuda_device, monkeypatch, exchange, H, B, T
         assert err <= 5e-5 * scale, (name, err, scale)
 
 
-@pytest.mark.parametrize("exchange", ["cluster", "l2"])
-def test_lstm_saturating_weights(cuda_device, monkeypatch, exchange):
-    monkeypatch.setenv("OPN_LSTM_EXCHANGE", exchange)
-    B, T, I, H = 9, 40, 90, 256
+@pytest.mark.parametrize("flavour", LSTM_FLAVOURS)
+@pytest.mark.parametrize("H", [256, 512])
+def test_lstm_saturating_weights(cuda_device, monkeypatch, flavour, H):
+    _set_lstm_flavour(monkeypatch, flavour, H)
+    B, T, I = 9, 40, 90
     x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=7, scale=8.0)
     xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
     ref = oracle.lstm_layer(xr, wir, whr)
@@ -152,11 +164,11 @@ def test_lstm_saturating_weights(cuda_device, monkeypatch, exchange):
         assert (got.cpu().double() - want).abs().max().item() <= 1e-3 * max(1.0, want.abs().max().item())
 
 
-@pytest.mark.parametrize("exchange", ["cluster", "l2"])
-@pytest.mark.parametrize("H,T", [(256, 300), (128, 120)])
-def test_lstm_long_sequence_both_exchanges(cuda_device, monkeypatch, exchange, H, T):
-    """T = 300 at the OPNet LSTM1 shape: 299 exchanges per launch, every ring / inbox slot reused ~150 times."""
-    monkeypatch.setenv("OPN_LSTM_EXCHANGE", exchange)
+@pytest.mark.parametrize("flavour", LSTM_FLAVOURS)
+@pytest.mark.parametrize("H,T", [(512, 300), (256, 300), (128, 120)])
+def test_lstm_long_sequence_all_flavours(cuda_device, monkeypatch, flavour, H, T):
+    """T = 300 at the OPNet LSTM shapes: 299 exchanges per launch, every ring / inbox slot reused ~150 times."""
+    _set_lstm_flavour(monkeypatch, flavour, H)
     B, I = 32, 90
     x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=31)
     dh = dh * 0.01
@@ -167,9 +179,11 @@ def test_lstm_long_sequence_both_exchanges(cuda_device, monkeypatch, exchange, H
     out = ops.lstm_layer(xg, wig, whg)
     out.backward(dh.to(cuda_device))
     assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5
+    print(f"\n[{flavour} H={H} T={T}] max|h - ref| = {(out.detach().cpu().double() - ref.detach()).abs().max().item():.3e}")
     for name, got, want in (("dx", xg.grad, xr.grad), ("dw_ih", wig.grad, wir.grad), ("dw_hh", whg.grad, whr.grad)):
         scale = max(1.0, want.abs().max().item())
         err = (got.cpu().double() - want).abs().max().item()
+        print(f"   {name}: err {err:.3e} (scale {scale:.3e})")
         assert err <= 1e-4 * scale, (name, err, scale)
 
 

@@ -8,7 +8,7 @@ lib = _lib.load(); dev = torch.device("cuda:0")
 T = 300
 import itertools
 HS = [int(x) for x in os.environ.get("HS", "256,512").split(",")]
-print("exchange =", os.environ.get("OPN_LSTM_EXCHANGE", "(default)"))
+print("math =", os.environ.get("OPN_LSTM_MATH", "(default)"), " exchange =", os.environ.get("OPN_LSTM_EXCHANGE", "(default)"))
 for B, H in itertools.product([int(x) for x in os.environ.get("BS", "32").split(",")], HS):
     xp = torch.randn(B, T, 4 * H, device=dev) * 0.5
     whh = (torch.rand(4 * H, H, device=dev) * 2 - 1) / (H ** 0.5)
