@@ -277,7 +277,7 @@ def run_ours(args):
                 alg = 4 * (rows * (4 * H + H + H + 4 * H) + 4 * H * H)
             kern[name] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9,
                           "us_per_step": ms * 1e3 / T,
-                          "ffma_tflops": 2.0 * rows * 4 * H * H / (ms * 1e-3) / 1e12}
+                          "matvec_tflops_fp32_equiv": 2.0 * rows * 4 * H * H / (ms * 1e-3) / 1e12}
     dom = max(kern, key=lambda k: kern[k]["ms"])
     hbm_peak = float(peaks["hbm_gbs"])
     traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
@@ -287,9 +287,9 @@ def run_ours(args):
             traffic = json.load(f).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "the persistent recurrences are step-latency bound (300 dependent steps, inter-CTA exchange "
-                        "1-1.3 us/step) with the FP32 FMA pipe behind it, not HBM bound: DESIGN.md section 3.1/5; "
-                        "per-kernel detail in 'kernels'",
+                "note": "the persistent recurrences are step-latency bound (300 dependent steps; the inter-CTA exchange "
+                        "through L2 is ~1 us of each ~2.3 us step, the split-fp16 HMMA matvec 0.2-0.5 us), not HBM "
+                        "bound: DESIGN.md section 3.1/5; per-kernel detail in 'kernels'",
                 "whole_step_algorithmic_gbs": (31700.0 * B_PER_GPU * T + 17.05e6) / (ms_per_step * 1e-3) / 1e9}
 
     # CPU baseline: bounded sample of the same workload on the host cores

@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_ulonglong, c_void_p, POINTER
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libopnet_b200.so")
+# OPN_B200_LIB selects a development variant of the library (e.g. the phase-counter build); never a fallback
+LIB_PATH = os.environ.get("OPN_B200_LIB") or os.path.join(_PKG, "lib", "libopnet_b200.so")
 
 OPN_OK = 0
 OPN_ERR_TIMEOUT = -4

@@ -42,16 +42,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), lib_path: str = LIB_PATH) -> str:
+    """defines / lib_path: development variants (e.g. -DOPN_LSTM_PHASES into lib/libopnet_b200_phases.so)."""
+    if not force and not defines and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
+    tag = "" if lib_path == LIB_PATH else "." + os.path.basename(lib_path).split(".")[0]
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIB_DIR, src.replace(".cu", tag + ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -62,13 +64,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if proc.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    link = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
         raise RuntimeError("linking libopnet_b200.so failed")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--phases" in sys.argv:  # development variant with per-phase cycle counters in the recurrence kernels
+        print(build(force=True, defines=["OPN_LSTM_PHASES"], lib_path=os.path.join(LIB_DIR, "libopnet_b200_phases.so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

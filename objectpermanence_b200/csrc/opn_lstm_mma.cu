@@ -27,6 +27,30 @@
 
 #include "opn_lstm_common.cuh"
 
+// Optional per-phase cycle accounting of the step loop (development builds: -DOPN_LSTM_PHASES, read back with
+// tools/lstm_phases.py): thread 0 of CTA 0 and CTA 77 sums clock64() deltas between the PH(i) marks into
+// status words 64.. / 128..
+#ifdef OPN_LSTM_PHASES
+#define PH_DECL long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ph_last = clock64();
+#define PH(i)                                   \
+    do {                                        \
+        const long long now__ = clock64();      \
+        ph_acc[i] += now__ - ph_last;           \
+        ph_last = now__;                        \
+    } while (0)
+#define PH_STORE(status)                                                                             \
+    do {                                                                                             \
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {                             \
+            unsigned long long* o = reinterpret_cast<unsigned long long*>(status) + (blockIdx.x ? 64 : 32); \
+            for (int i = 0; i < 8; ++i) o[i] = (unsigned long long)ph_acc[i];                        \
+        }                                                                                            \
+    } while (0)
+#else
+#define PH_DECL
+#define PH(i)
+#define PH_STORE(status)
+#endif
+
 namespace opn {
 
 namespace {
@@ -45,6 +69,16 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx + rcp.approx): absolute error < 3e-7 over the whole range,
+// saturates correctly at +-1 (exp -> inf gives 2/inf = 0).  sigmoid(x) = 0.5 + 0.5 tanh(x/2), so the three gate
+// non-linearities of a lane pair are one branch-free formula: act = s * tanh(s * a) + o with (s, o) = (1, 0) or
+// (0.5, 0.5).  (The accurate expf / tanhf sequence of the FP32-FMA kernels cost ~550 clocks per step here.)
+__device__ __forceinline__ float tanh_sfu(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
 // power-of-two scale bringing `amax` into [2^(target-1), 2^target); 1 for amax == 0
@@ -146,14 +180,29 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
     }
 
     // ---- pointwise ownership: two lanes per (unit, video) cell, lane gh computes gates 2gh, 2gh+1 -----------
-    const int cell = tid >> 1, gh = tid & 1;
-    const int ul = cell >> 3, bl = cell & 7;
+    // The cells are dealt to the lanes so that the values of one fragment vector of the exchange tile meet in one
+    // warp and are published with a single vector store (4x / 2x fewer L2 store transactions than scalar words):
+    //   U = 16: a vector = units {2q, 2q+1, 2q+8, 2q+9} of one video; warp w: q = w>>1, videos 4*(w&1)..+3;
+    //           lane = (video bq : 2 bits | j : 2 bits | gh), unit = 2q + (j&1) + 8*(j>>1)
+    //   U =  8: the CTA owns half a k-step: a pair = units {2q, 2q+1}; warp w: q = w; lane = (video : 3 | j : 1 | gh)
+    const int gh = lane & 1;
+    int ul, bl;
+    if (U == 16) {
+        const int j = (lane >> 1) & 3;
+        ul = 2 * (warp >> 1) + (j & 1) + 8 * (j >> 1);
+        bl = 4 * (warp & 1) + (lane >> 3);
+    } else {
+        ul = 2 * warp + ((lane >> 1) & 1);
+        bl = lane >> 2;
+    }
+    const bool leader = (U == 16) ? ((lane & 7) == 0) : ((lane & 3) == 0);  // stores the vector of its lane group
     const int u = u0 + ul;
     const int bb = b0 + bl;
     const bool valid = bb < p.B;
     const size_t row0 = (size_t)(valid ? bb : 0) * T;
     const float* xp_ptr = p.xproj + row0 * (4 * H) + (size_t)(2 * gh) * H + u;
-    const int pub_word = frag_word(bl, u);
+    const int pub_word = frag_word(bl, u);  // leader: first word of the vector (units 2q.. of the k-step half)
+    const float s0 = gh ? 1.0f : 0.5f;
 
     float c_state = 0.0f;
     int my_abort = 0;
@@ -164,8 +213,10 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
     }
     __syncthreads();
 
+    PH_DECL
     for (int t = 0; t < T; ++t) {
         float a0 = xp0, a1 = xp1;
+        PH(0);  // publish + stash stores + prefetch of the previous step
         if (t > 0) {
             // ---- h_{t-1}: poll this thread's fragment vectors, split, store as fp16 fragments -----------------
             const uint32_t par = step_parity(t - 1);
@@ -174,6 +225,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
             uint4 v[NV];
             if (!gather_flagged(v, [&](int i) { return src + (size_t)(tid + NT * i) * 4; }, vec_valid, par, p.status, t))
                 my_abort = 1;
+            PH(1);  // poll
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 if (vec_valid(i)) {
@@ -184,6 +236,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
                 }
             }
             if (__syncthreads_or(my_abort)) break;
+            PH(2);  // split + STS + barrier
 
             // ---- this warp's 16 rows x its K half: hi*hi on two alternating chains, cross terms on two more --
             float dm0[4] = {0.f, 0.f, 0.f, 0.f}, dm1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -205,15 +258,17 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
                                            ((dm0[3] + dm1[3]) + (ds0[3] + ds1[3])) * winv);
             *reinterpret_cast<float2*>(&d_s[kp][lr_a][2 * tq]) = lo2;
             *reinterpret_cast<float2*>(&d_s[kp][lr_b][2 * tq]) = hi2;
+            PH(3);  // MMAs
             __syncthreads();
+            PH(4);  // barrier
             const int lr0 = ul * 4 + 2 * gh;
             a0 += d_s[0][lr0][bl] + d_s[1][lr0][bl];
             a1 += d_s[0][lr0 + 1][bl] + d_s[1][lr0 + 1][bl];
         }
 
         // fused pointwise: gate activations, cell update
-        const float act0 = gh ? tanhf(a0) : sigmoid_acc(a0);  // gh=0: i      gh=1: g
-        const float act1 = sigmoid_acc(a1);                    // gh=0: f      gh=1: o
+        const float act0 = fmaf(s0, tanh_sfu(s0 * a0), 1.0f - s0);      // gh=0: i = sigmoid   gh=1: g = tanh
+        const float act1 = fmaf(0.5f, tanh_sfu(0.5f * a1), 0.5f);       // gh=0: f             gh=1: o
         const float oth0 = __shfl_xor_sync(0xffffffffu, act0, 1);
         const float oth1 = __shfl_xor_sync(0xffffffffu, act1, 1);
         const float gi = gh ? oth0 : act0;
@@ -221,11 +276,27 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
         const float gg = gh ? act0 : oth0;
         const float go = gh ? act1 : oth1;
         c_state = fmaf(gf, c_state, gi * gg);
-        const float hval = go * tanhf(c_state);
+        const float hval = go * tanh_sfu(c_state);
+        PH(5);  // pointwise
+        // critical path first: publish h_t to the other CTAs of this batch group (one vector per lane group)
+        {
+            const uint32_t par = step_parity(t);
+            const uint32_t w0 = flagged(hval, par);
+            const uint32_t w1 = __shfl_xor_sync(0xffffffffu, w0, 2);
+            uint32_t* dst = ring + (size_t)(t & 1) * (kGroup * H) + pub_word;
+            if (U == 16) {
+                const uint32_t w2 = __shfl_xor_sync(0xffffffffu, w0, 4);
+                const uint32_t w3 = __shfl_xor_sync(0xffffffffu, w0, 6);
+                if (leader && valid && t + 1 < T)
+                    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(w0), "r"(w1), "r"(w2),
+                                 "r"(w3)
+                                 : "memory");
+            } else {
+                if (leader && valid && t + 1 < T)
+                    asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1,%2};" ::"l"(dst), "r"(w0), "r"(w1) : "memory");
+            }
+        }
         if (valid) {
-            // critical path first: publish h_t to the other CTAs of this batch group
-            if (gh == 0 && t + 1 < T)
-                st_flagged(ring + (size_t)(t & 1) * (kGroup * H) + pub_word, hval, step_parity(t));
             const size_t row = row0 + t;
             if (gh == 0) {
                 p.hs[row * H + u] = hval;
@@ -246,6 +317,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
             }
         }
     }
+    PH_STORE(p.status);
 }
 
 // ------------------------------------------------------------------------------------
@@ -337,30 +409,49 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
     const int da_word = 4 * ((lr_pair >> 4) * 32 + bl * 4 + (((lr_pair & 15) & 7) >> 1)) + ((lr_pair & 15) >> 3);
 
     float dc_carry = 0.0f, dh_rec = 0.0f;
+    // stash of the step being processed (s*) and of the next one (n*): prefetched two steps ahead, the loads of a
+    // step are issued ~2 step times before their first use (one step ahead was measured to stall the cell backward
+    // for ~1000 clocks: the stash streams from HBM behind the polling traffic)
     float si = 0.f, sf = 0.f, sg = 0.f, so = 0.f, sc = 0.f, scp = 0.f, sdh = 0.f;
-    auto load_stash = [&](int t) {
+    float ni = 0.f, nf = 0.f, ng = 0.f, no = 0.f, ndh = 0.f;
+    auto load_next = [&](int t) {  // row t into n*; the cell value of row t is already held in scp
         const size_t row = row0 + t;
+        const float* gp = p.gates + row * (size_t)(4 * H) + u;
+        ni = __ldg(gp);
+        nf = __ldg(gp + H);
+        ng = __ldg(gp + 2 * H);
+        no = __ldg(gp + 3 * H);
+        ndh = __ldg(p.dh_out + row * H + u);
+    };
+    float ncp = 0.f;  // cells[t-2] for the step after next
+    if (valid) {
+        const size_t row = row0 + (T - 1);
         const float* gp = p.gates + row * (size_t)(4 * H) + u;
         si = __ldg(gp);
         sf = __ldg(gp + H);
         sg = __ldg(gp + 2 * H);
         so = __ldg(gp + 3 * H);
         sc = __ldg(p.cells + row * H + u);
-        scp = (t > 0) ? __ldg(p.cells + (row - 1) * H + u) : 0.0f;
+        scp = (T > 1) ? __ldg(p.cells + (row - 1) * H + u) : 0.0f;
         sdh = __ldg(p.dh_out + row * H + u);
-    };
-    if (valid) load_stash(T - 1);
+        if (T > 1) {
+            load_next(T - 2);
+            ncp = (T > 2) ? __ldg(p.cells + (row - 2) * H + u) : 0.0f;
+        }
+    }
     __syncthreads();
 
     int my_abort = 0;
 
+    PH_DECL
     for (int t = T - 1; t >= 0; --t) {
         const int s = T - 1 - t;  // step number of the reverse recurrence: ring slot s&1, parity of s
         const int buf = s & 1;
+        PH(0);  // reduction of the gathered partials
         // ---- 1. cell backward for the CTA's own units ---------------------------------------------------
         if (valid) {
             const float dh = sdh + dh_rec;
-            const float tc = tanhf(sc);
+            const float tc = tanh_sfu(sc);
             const float d_o = dh * tc;
             const float dc = fmaf(dh * so, 1.0f - tc * tc, dc_carry);
             const float d_i = dc * sg;
@@ -392,11 +483,20 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
                 w[0] = hi;
                 w[2] = lo;
                 if (ul == 0 && half == 0) dainv_s[buf][bl] = inv2 * winv;
-                load_stash(t - 1);  // prefetch: lands while the matvec and the exchange run
+                // rotate: step t-1 becomes current, issue the loads of step t-2
+                si = ni, sf = nf, sg = ng, so = no, sdh = ndh;
+                sc = scp;
+                scp = ncp;
+                if (t > 1) {
+                    load_next(t - 2);
+                    ncp = (t > 2) ? __ldg(p.cells + (row0 + t - 3) * H + u) : 0.0f;
+                }
             }
         }
         if (t == 0) break;
+        PH(1);  // cell backward
         if (__syncthreads_or(my_abort)) break;  // dafrag_s[buf] complete (double buffered: one barrier per step)
+        PH(2);  // barrier
 
         // ---- 2. partial[k][b] over the own rows; publish ------------------------------------------------
         const uint32_t par = step_parity(s);
@@ -430,6 +530,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
             }
         }
 
+        PH(3);  // MMAs + publish
         // ---- 3. reduce-scatter: sum the producers' partials for the own units ---------------------------
         {
             uint4 v[4];
@@ -443,6 +544,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
                     v, [&](int i) { return src + ((size_t)vec_b(i) * NS * VPC + vec_id(i)) * 4; }, vec_valid, par,
                     p.status, t))
                 my_abort = 1;
+            PH(4);  // poll
             float f[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -473,6 +575,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
             }
         }
     }
+    PH_STORE(p.status);
 }
 
 }  // namespace
