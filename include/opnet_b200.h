@@ -116,6 +116,22 @@ OPN_API int opn_wtt_bwd(int64_t B, int64_t T, int64_t H1, const float* boxes, co
                 const float* d_frames_boxes, const float* d_logits_bpt, float* d_logits, float* d_hs1,
                 void* stream);
 
+/* ---- OPNet fused forward -------------------------------------------------------------
+ * LSTM1 (x-projection given), the who-to-track stage and LSTM2 (its K = 6 input projection included) as ONE
+ * persistent kernel that advances all three frame by frame: the function of opn_lstm_fwd(H1) -> opn_wtt_fwd ->
+ * opn_sgemm(W_ih2) -> opn_lstm_fwd(H2), with the same outputs (so the backward entry points above apply
+ * unchanged), for the shipped OPNet config H1 = 256, H2 = 512 (OPN_ERR_UNSUPPORTED otherwise).
+ * Replaces: OPNet.forward, baselines/learned_models.py:36-46 (configs/opnet_model_config.json).
+ *   boxes [B,T,15,6], xproj1 [B,T,4*H1] = boxes W_ih1^T, w_hh1 [4*H1,H1], w_pred [15,H1], w_ih2 [4*H2,6],
+ *   w_hh2 [4*H2,H2]  ->  hs1 [B,T,H1], logits_bpt [B,15,T], probs [B,T,15], frames_boxes [B,T,6], hs2 [B,T,H2];
+ *   gates1/cells1/gates2/cells2: stash for the backward pass, all given or all NULL (inference).
+ * workspace: opn_opnet_fwd_workspace_bytes(B,T) bytes of scratch (status word as for opn_lstm_status, two rings). */
+OPN_API int64_t opn_opnet_fwd_workspace_bytes(int64_t B, int64_t T);
+OPN_API int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1, int64_t H2, const float* boxes, const float* xproj1,
+                  const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2, float* hs1,
+                  float* gates1, float* cells1, float* logits_bpt, float* probs, float* frames_boxes, float* hs2,
+                  float* gates2, float* cells2, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- element-wise / row-wise helpers (transformer_lstm encoder, MLP variant) -------- */
 /* dy[i] = (y[i] > 0) ? dy[i] : 0   (ReLU backward, in place on dy) */
 OPN_API int opn_relu_bwd(int64_t n, const float* y, float* dy, void* stream);

@@ -16,8 +16,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libopnet_b200.so")
-SOURCES = ["opn_api.cu", "opn_lstm.cu", "opn_lstm_mma.cu", "opn_gemm.cu", "opn_gemm_tc.cu", "opn_pointwise.cu"]
-HEADERS = [os.path.join(CSRC, "opn_common.cuh"), os.path.join(CSRC, "opn_lstm_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "opnet_b200.h")]
+SOURCES = ["opn_api.cu", "opn_lstm.cu", "opn_lstm_mma.cu", "opn_opnet_fused.cu", "opn_gemm.cu", "opn_gemm_tc.cu", "opn_pointwise.cu"]
+HEADERS = [os.path.join(CSRC, "opn_common.cuh"), os.path.join(CSRC, "opn_lstm_common.cuh"), os.path.join(CSRC, "opn_mma_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "opnet_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -73,7 +73,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), lib_path: str 
 
 
 if __name__ == "__main__":
-    if "--phases" in sys.argv:  # development variant with per-phase cycle counters in the recurrence kernels
+    if "--exp" in sys.argv:  # experiment variants: --exp NAME DEFINE[=VALUE] ...
+        i = sys.argv.index("--exp")
+        print(build(force=True, defines=sys.argv[i + 2:], lib_path=os.path.join(LIB_DIR, f"libopnet_b200_{sys.argv[i + 1]}.so")))
+    elif "--phases" in sys.argv:  # development variant with per-phase cycle counters in the recurrence kernels
         print(build(force=True, defines=["OPN_LSTM_PHASES"], lib_path=os.path.join(LIB_DIR, "libopnet_b200_phases.so")))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

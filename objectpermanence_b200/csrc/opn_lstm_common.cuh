@@ -4,6 +4,10 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "opn_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -171,12 +175,46 @@ int max_coresident(Kernel kernel, int threads, size_t smem, int* out) {
 
 // Ring flavour: the n_slices CTAs of a batch group exchange through global memory, so they must be co-resident:
 // cooperative launches of as many whole batch groups as fit on the device.
+// cluster_size > 1: the CTAs are additionally grouped into thread-block clusters of that many consecutive slices
+// (n_slices must be a multiple of it): cooperative launch + cluster dimension.
 template <typename Kernel, typename Params>
 int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem, int64_t B, cudaStream_t stream,
-                const char* what) {
-    int cap = 0;
-    int rc = max_coresident(kernel, threads, smem, &cap);
-    if (rc != OPN_OK) return rc;
+                const char* what, int cluster_size = 1) {
+    // the capacity of the device for this kernel is queried once (the occupancy calls cost 0.1-1 ms of host time each)
+    static std::mutex cache_mutex;
+    static std::map<std::pair<const void*, int>, int> cap_cache;   // (kernel, device) -> co-resident CTAs
+    int dev = 0;
+    OPN_CUDA(cudaGetDevice(&dev));
+    const std::pair<const void*, int> key((const void*)kernel, dev);
+    int cap = -1;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        auto it = cap_cache.find(key);
+        if (it != cap_cache.end()) cap = it->second;
+    }
+    if (cap < 0) {
+        int rc = max_coresident(kernel, threads, smem, &cap);
+        if (rc != OPN_OK) return rc;
+        if (cluster_size > 1) {
+            // whole clusters must fit: ask the occupancy calculator for the cluster flavour
+            cudaLaunchConfig_t probe = {};
+            probe.gridDim = dim3((unsigned)n_slices);
+            probe.blockDim = dim3((unsigned)threads);
+            probe.dynamicSmemBytes = smem;
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeClusterDimension;
+            pa[0].val.clusterDim.x = (unsigned)cluster_size;
+            pa[0].val.clusterDim.y = 1;
+            pa[0].val.clusterDim.z = 1;
+            probe.attrs = pa;
+            probe.numAttrs = 1;
+            int max_clusters = 0;
+            OPN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &probe));
+            if (max_clusters * cluster_size < cap) cap = max_clusters * cluster_size;
+        }
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        cap_cache[key] = cap;
+    }
     const int groups = (int)((B + kGroup - 1) / kGroup);
     const int per_launch = cap / n_slices;
     if (per_launch < 1) {
@@ -187,9 +225,27 @@ int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem,
     for (int g0 = 0; g0 < groups; g0 += per_launch) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
-        void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(n_slices * ng), dim3(threads), args, smem,
-                                             stream));
+        if (cluster_size > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(n_slices * ng));
+            cfg.blockDim = dim3((unsigned)threads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cluster_size;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeCooperative;
+            attr[1].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 2;
+            OPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+        } else {
+            void* args[] = {(void*)&p};
+            OPN_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(n_slices * ng), dim3(threads), args, smem,
+                                                 stream));
+        }
         count_launch();
     }
     return OPN_OK;

@@ -189,37 +189,42 @@ class LstmLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dhs):
         x, w_ih, w_hh, hs, gates, cells = ctx.saved_tensors
-        B, T, I = x.shape
-        H = w_hh.shape[1]
-        lib = _lib.load()
-        dev = x.device
-        dhs = dhs.contiguous()
-        dgates = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
-        ws = _lstm_workspace(B, T, H, dev)
-        rc = lib.opn_lstm_bwd(B, T, H, w_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dhs.data_ptr(),
-                              dgates.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
-        _lib.check(rc, "opn_lstm_bwd")
-        _lstm_check(ws, "opn_lstm_bwd")
-        dx = dw_ih = dw_hh = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            sgemm(dgates, w_ih, dx, trans_a=False, trans_b=False, M=B * T, N=I, K=4 * H, lda=4 * H, ldb=I, ldc=I)
-        if ctx.needs_input_grad[1]:
-            dw_ih = torch.empty_like(w_ih)
-            sgemm(dgates, x, dw_ih, trans_a=True, trans_b=False, M=4 * H, N=I, K=B * T, lda=4 * H, ldb=I, ldc=I)
-        if ctx.needs_input_grad[2]:
-            dw_hh = torch.empty_like(w_hh)
-            if T > 1:
-                # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1].  Contract the flat row pairs (r+1, r) over all
-                # B*T-1 rows, then take out the B-1 pairs that straddle two videos (rows b*T and b*T-1).
-                sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B * T - 1, lda=4 * H, ldb=H,
-                      ldc=H, a_off=4 * H)
-                if B > 1:
-                    sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B - 1, lda=T * 4 * H,
-                          ldb=T * H, ldc=H, alpha=-1.0, beta=1.0, a_off=T * 4 * H, b_off=(T - 1) * H)
-            else:
-                dw_hh.zero_()
-        return dx, dw_ih, dw_hh
+        return _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, ctx.needs_input_grad)
+
+
+def _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, needs):
+    """Reverse recurrence + the three time-parallel contractions of one LSTM layer -> (dx, dW_ih, dW_hh)."""
+    B, T, I = x.shape
+    H = w_hh.shape[1]
+    lib = _lib.load()
+    dev = x.device
+    dhs = dhs.contiguous()
+    dgates = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
+    ws = _lstm_workspace(B, T, H, dev)
+    rc = lib.opn_lstm_bwd(B, T, H, w_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dhs.data_ptr(),
+                          dgates.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "opn_lstm_bwd")
+    _lstm_check(ws, "opn_lstm_bwd")
+    dx = dw_ih = dw_hh = None
+    if needs[0]:
+        dx = torch.empty_like(x)
+        sgemm(dgates, w_ih, dx, trans_a=False, trans_b=False, M=B * T, N=I, K=4 * H, lda=4 * H, ldb=I, ldc=I)
+    if needs[1]:
+        dw_ih = torch.empty_like(w_ih)
+        sgemm(dgates, x, dw_ih, trans_a=True, trans_b=False, M=4 * H, N=I, K=B * T, lda=4 * H, ldb=I, ldc=I)
+    if needs[2]:
+        dw_hh = torch.empty_like(w_hh)
+        if T > 1:
+            # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1].  Contract the flat row pairs (r+1, r) over all
+            # B*T-1 rows, then take out the B-1 pairs that straddle two videos (rows b*T and b*T-1).
+            sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B * T - 1, lda=4 * H, ldb=H,
+                  ldc=H, a_off=4 * H)
+            if B > 1:
+                sgemm(dgates, hs, dw_hh, trans_a=True, trans_b=False, M=4 * H, N=H, K=B - 1, lda=T * 4 * H,
+                      ldb=T * H, ldc=H, alpha=-1.0, beta=1.0, a_off=T * 4 * H, b_off=(T - 1) * H)
+        else:
+            dw_hh.zero_()
+    return dx, dw_ih, dw_hh
 
 
 class WhoToTrackFn(torch.autograd.Function):
@@ -249,26 +254,91 @@ class WhoToTrackFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfb, dlogits):
         boxes, hs1, w_pred, probs = ctx.saved_tensors
-        B, T, NO, F = boxes.shape
-        H1 = hs1.shape[-1]
-        dev = boxes.device
-        if dfb is None:
-            dfb = torch.zeros(B, T, 6, device=dev, dtype=torch.float32)
-        dfb = dfb.contiguous()
-        dl_up = dlogits.contiguous() if dlogits is not None else None
-        dl = torch.empty(B, T, 15, device=dev, dtype=torch.float32)
-        dhs1 = torch.empty_like(hs1)
-        rc = _lib.load().opn_wtt_bwd(B, T, H1, boxes.data_ptr(), probs.data_ptr(), w_pred.data_ptr(), dfb.data_ptr(),
-                                     _ptr(dl_up), dl.data_ptr(), dhs1.data_ptr(), _stream())
-        _lib.check(rc, "opn_wtt_bwd")
-        dw = None
-        if ctx.needs_input_grad[2]:
-            # dW_pred^T [H1,15] = hs1^T dl: contracted in the transposed orientation so that the long dimension
-            # (H1) maps to the 128-row tile and the 15 objects to the 16-wide one (as M=15 it ran 7x slower)
-            dw_t = torch.empty(H1, 15, device=dev, dtype=torch.float32)
-            sgemm(hs1, dl, dw_t, trans_a=True, trans_b=False, M=H1, N=15, K=B * T, lda=H1, ldb=15, ldc=15)
-            dw = dw_t.t()
+        dhs1, dw = _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, ctx.needs_input_grad[2])
         return None, dhs1, dw
+
+
+def _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, need_dw):
+    """who-to-track backward -> (d hs1, dW_pred)."""
+    B, T, NO, F = boxes.shape
+    H1 = hs1.shape[-1]
+    dev = boxes.device
+    if dfb is None:
+        dfb = torch.zeros(B, T, 6, device=dev, dtype=torch.float32)
+    dfb = dfb.contiguous()
+    dl_up = dlogits.contiguous() if dlogits is not None else None
+    dl = torch.empty(B, T, 15, device=dev, dtype=torch.float32)
+    dhs1 = torch.empty_like(hs1)
+    rc = _lib.load().opn_wtt_bwd(B, T, H1, boxes.data_ptr(), probs.data_ptr(), w_pred.data_ptr(), dfb.data_ptr(),
+                                 _ptr(dl_up), dl.data_ptr(), dhs1.data_ptr(), _stream())
+    _lib.check(rc, "opn_wtt_bwd")
+    dw = None
+    if need_dw:
+        # dW_pred^T [H1,15] = hs1^T dl: contracted in the transposed orientation so that the long dimension
+        # (H1) maps to the 128-row tile and the 15 objects to the 16-wide one (as M=15 it ran 7x slower)
+        dw_t = torch.empty(H1, 15, device=dev, dtype=torch.float32)
+        sgemm(hs1, dl, dw_t, trans_a=True, trans_b=False, M=H1, N=15, K=B * T, lda=H1, ldb=15, ldc=15)
+        dw = dw_t.t()
+    return dhs1, dw
+
+
+class OPNetTrunkFn(torch.autograd.Function):
+    """OPNet up to the bbox head (baselines/learned_models.py:36-46) with the forward as ONE persistent kernel:
+    LSTM1, the who-to-track head and LSTM2 advance frame by frame together (csrc/opn_opnet_fused.cu), each hiding
+    the other's exchange latency.  Shipped config only (H1 = 256, H2 = 512).  The stash it leaves is that of the
+    separate kernels, so the backward pass is theirs: reverse LSTM2, who-to-track backward, reverse LSTM1 and the
+    time-parallel weight-gradient contractions."""
+
+    @staticmethod
+    def forward(ctx, boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2):
+        _require_cuda(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2)
+        boxes = boxes.contiguous()
+        w_ih1, w_hh1, w_pred, w_ih2, w_hh2 = [w.contiguous() for w in (w_ih1, w_hh1, w_pred, w_ih2, w_hh2)]
+        B, T, NO, F = boxes.shape
+        H1, H2 = w_hh1.shape[1], w_hh2.shape[1]
+        lib = _lib.load()
+        dev = boxes.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        xproj1 = torch.empty(B, T, 4 * H1, **f32)
+        sgemm(boxes, w_ih1, xproj1, trans_a=False, trans_b=True, M=B * T, N=4 * H1, K=NO * F, lda=NO * F, ldb=NO * F,
+              ldc=4 * H1)
+        need_grad = any(ctx.needs_input_grad)
+        hs1 = torch.empty(B, T, H1, **f32)
+        hs2 = torch.empty(B, T, H2, **f32)
+        logits = torch.empty(B, 15, T, **f32)
+        probs = torch.empty(B, T, 15, **f32)
+        fb = torch.empty(B, T, 6, **f32)
+        gates1 = cells1 = gates2 = cells2 = None
+        if need_grad:
+            gates1 = torch.empty(B, T, 4 * H1, **f32)
+            cells1 = torch.empty(B, T, H1, **f32)
+            gates2 = torch.empty(B, T, 4 * H2, **f32)
+            cells2 = torch.empty(B, T, H2, **f32)
+        ws = torch.empty(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+        rc = lib.opn_opnet_fwd(B, T, H1, H2, boxes.data_ptr(), xproj1.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
+                               w_ih2.data_ptr(), w_hh2.data_ptr(), hs1.data_ptr(), _ptr(gates1), _ptr(cells1),
+                               logits.data_ptr(), probs.data_ptr(), fb.data_ptr(), hs2.data_ptr(), _ptr(gates2),
+                               _ptr(cells2), ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "opn_opnet_fwd")
+        _lstm_check(ws, "opn_opnet_fwd")
+        if need_grad:
+            ctx.save_for_backward(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2, hs1, gates1, cells1, probs, fb, hs2,
+                                  gates2, cells2)
+        return hs2, logits
+
+    @staticmethod
+    def backward(ctx, dhs2, dlogits):
+        (boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2, hs1, gates1, cells1, probs, fb, hs2, gates2,
+         cells2) = ctx.saved_tensors
+        B, T = boxes.shape[:2]
+        need = ctx.needs_input_grad
+        if dhs2 is None:
+            dhs2 = torch.zeros_like(hs2)
+        dfb, dw_ih2, dw_hh2 = _lstm_backward(fb, w_ih2, w_hh2, hs2, gates2, cells2, dhs2, (True, need[4], need[5]))
+        dhs1, dw_pred = _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, need[3])
+        x1 = boxes.reshape(B, T, -1)
+        _, dw_ih1, dw_hh1 = _lstm_backward(x1, w_ih1, w_hh1, hs1, gates1, cells1, dhs1, (False, need[1], need[2]))
+        return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
 
 
 class AddLayerNormFn(torch.autograd.Function):
@@ -415,6 +485,16 @@ def lstm_layer(x, w_ih, w_hh):
 
 def who_to_track(boxes, hs1, w_pred):
     return WhoToTrackFn.apply(boxes, hs1, w_pred)
+
+
+def opnet_fused_available(h1: int, h2: int, pred_dim: int) -> bool:
+    """The fused OPNet forward exists for the shipped config; OPN_OPNET_FUSED=0 selects the separate kernels."""
+    return (h1, h2, pred_dim) == (256, 512, 15) and os.environ.get("OPN_OPNET_FUSED", "1") not in ("0", "")
+
+
+def opnet_trunk(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2):
+    """(hs2 [B,T,H2], who-to-track logits [B,15,T]) of OPNet through the fused forward kernel."""
+    return OPNetTrunkFn.apply(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2)
 
 
 def add_layer_norm(x, res, weight, bias, eps: float = 1e-5):

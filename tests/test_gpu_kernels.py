@@ -201,6 +201,53 @@ def test_lstm_unsupported_hidden_size(cuda_device):
         ops.lstm_layer(x.to(cuda_device), w_ih.to(cuda_device), w_hh.to(cuda_device))
 
 
+# ---- fused OPNet forward ----------------------------------------------------------------------
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (11, 37), (32, 64), (70, 9)])
+def test_opnet_fused_forward_matches_separate_kernels(cuda_device, monkeypatch, B, T):
+    """LSTM1 + who-to-track + LSTM2 as one persistent kernel against the chain of separate kernels and the fp64
+    oracle: outputs, every stash tensor the backward pass reads, and the gradients through both paths."""
+    H1, H2 = 256, 512
+    boxes = torch.rand(B, T, 15, 6, generator=torch.Generator().manual_seed(5 + B)) * (torch.rand(B, T, 15, 1) > 0.3)
+    w = {"ih1": _rand((4 * H1, 90), 1, 1 / math.sqrt(H1)), "hh1": _rand((4 * H1, H1), 2, 1 / math.sqrt(H1)),
+         "pred": _rand((15, H1), 3, 1 / math.sqrt(H1)), "ih2": _rand((4 * H2, 6), 4, 1 / math.sqrt(H2)),
+         "hh2": _rand((4 * H2, H2), 5, 1 / math.sqrt(H2))}
+    dh2 = _rand((B, T, H2), 6, 0.01)
+
+    def run(fused):
+        ws = {k: v.to(cuda_device).requires_grad_(True) for k, v in w.items()}
+        bx = boxes.to(cuda_device)
+        if fused:
+            h2, logits = ops.opnet_trunk(bx, ws["ih1"], ws["hh1"], ws["pred"], ws["ih2"], ws["hh2"])
+        else:
+            h1 = ops.lstm_layer(bx.reshape(B, T, -1), ws["ih1"], ws["hh1"])
+            fb, logits = ops.who_to_track(bx, h1, ws["pred"])
+            h2 = ops.lstm_layer(fb, ws["ih2"], ws["hh2"])
+        h2.backward(dh2.to(cuda_device))
+        return h2.detach().cpu(), logits.detach().cpu(), {k: v.grad.cpu() for k, v in ws.items()}
+
+    h2_f, lg_f, g_f = run(True)
+    h2_s, lg_s, g_s = run(False)
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    h1_r = oracle.lstm_layer(boxes.double().reshape(B, T, -1), wr["ih1"], wr["hh1"])
+    fb_r, lg_r = oracle.who_to_track(boxes.double(), h1_r, wr["pred"])
+    h2_r = oracle.lstm_layer(fb_r, wr["ih2"], wr["hh2"])
+    h2_r.backward(dh2.double())
+    assert (h2_f.double() - h2_r.detach()).abs().max().item() <= 2e-5
+    assert (lg_f.double() - lg_r.detach().permute(0, 2, 1)).abs().max().item() <= 2e-5
+    assert (h2_f - h2_s).abs().max().item() <= 1e-5 and (lg_f - lg_s).abs().max().item() <= 1e-5
+    for k in w:
+        want = wr[k].grad
+        scale = max(1.0, want.abs().max().item())
+        assert (g_f[k].double() - want).abs().max().item() <= 1e-4 * scale, k
+        assert (g_s[k].double() - want).abs().max().item() <= 1e-4 * scale, k
+
+
+def test_opnet_fused_forward_rejects_other_configs(cuda_device):
+    lib = _lib.load()
+    assert lib.opn_opnet_fwd(2, 2, 128, 512, *([None] * 16), 0, None) != 0
+    assert b"shipped OPNet config" in lib.opn_last_error()
+
+
 # ---- who-to-track ---------------------------------------------------------------------------
 @pytest.mark.parametrize("B,T,H1", [(1, 1, 32), (3, 11, 256), (5, 300, 64)])
 def test_who_to_track(cuda_device, B, T, H1):

@@ -27,3 +27,28 @@ for H in (256, 512):
             ph = words[off:off + 8].tolist()
             tot = sum(ph)
             print(f"H={H} {name} cta {cta}: total {tot / T:7.0f} clk/step | " + "  ".join(f"{l} {v / T:6.0f}" for l, v in zip(labels, ph) if l != "-"), flush=True)
+
+# fused OPNet forward
+B, H1, H2 = 32, 256, 512
+f32 = dict(device=dev, dtype=torch.float32)
+boxes = torch.rand(B, T, 15, 6, **f32)
+xp1 = torch.randn(B, T, 4 * H1, **f32) * 0.5
+w_hh1 = (torch.rand(4 * H1, H1, **f32) * 2 - 1) / H1 ** 0.5
+w_pred = (torch.rand(15, H1, **f32) * 2 - 1) / H1 ** 0.5
+w_ih2 = (torch.rand(4 * H2, 6, **f32) * 2 - 1) / H2 ** 0.5
+w_hh2 = (torch.rand(4 * H2, H2, **f32) * 2 - 1) / H2 ** 0.5
+hs1 = torch.empty(B, T, H1, **f32); g1 = torch.empty(B, T, 4 * H1, **f32); c1 = torch.empty(B, T, H1, **f32)
+hs2 = torch.empty(B, T, H2, **f32); g2 = torch.empty(B, T, 4 * H2, **f32); c2 = torch.empty(B, T, H2, **f32)
+lg = torch.empty(B, 15, T, **f32); pr = torch.empty(B, T, 15, **f32); fb = torch.empty(B, T, 6, **f32)
+ws = torch.zeros(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+s = torch.cuda.current_stream().cuda_stream
+for _ in range(2):
+    _lib.check(lib.opn_opnet_fwd(B, T, H1, H2, boxes.data_ptr(), xp1.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(), w_ih2.data_ptr(), w_hh2.data_ptr(),
+                                 hs1.data_ptr(), g1.data_ptr(), c1.data_ptr(), lg.data_ptr(), pr.data_ptr(), fb.data_ptr(), hs2.data_ptr(), g2.data_ptr(), c2.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), s))
+torch.cuda.synchronize()
+words = ws[:4096].view(torch.int64).cpu()
+FUSED = ["publish2+stores", "poll h1", "split+barrier", "MMA1+head+barrier", "pointwise1/head", "poll h2", "split+bar+MMA2+bar", "pointwise2"]
+for cta, off in ((0, 32), (77, 64)):
+    ph = words[off:off + 8].tolist()
+    print(f"fused fwd cta {cta}: total {sum(ph) / T:7.0f} clk/frame | " + "  ".join(f"{l} {v / T:6.0f}" for l, v in zip(FUSED, ph)), flush=True)
