@@ -4,6 +4,8 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <utility>
@@ -239,7 +241,10 @@ int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem,
             attr[1].id = cudaLaunchAttributeCooperative;
             attr[1].val.cooperative = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 2;
+            // OPN_NO_COOP_CLUSTER=1: plain cluster launch (Nsight Compute cannot replay cooperative cluster launches);
+            // the grid never exceeds the co-resident capacity computed above, the time-outs cover the rest
+            const char* e = getenv("OPN_NO_COOP_CLUSTER");
+            cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
             OPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
         } else {
             void* args[] = {(void*)&p};

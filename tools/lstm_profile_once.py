@@ -16,3 +16,13 @@ for H in (256, 512):
     _lib.check(lib.opn_lstm_bwd(B, T, H, whh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dh.data_ptr(), dg.data_ptr(), ws.data_ptr(), ws.numel(), s))
     torch.cuda.synchronize()
 print("done")
+# fused OPNet forward, once
+H1, H2 = 256, 512
+f32 = dict(device=dev, dtype=torch.float32)
+bx = torch.rand(B, T, 15, 6, **f32); xp1 = torch.randn(B, T, 4 * H1, **f32) * 0.5
+w = [(torch.rand(*shape, **f32) * 2 - 1) / (h ** 0.5) for shape, h in (((4 * H1, H1), H1), ((15, H1), H1), ((4 * H2, 6), H2), ((4 * H2, H2), H2))]
+outs = [torch.empty(*shape, **f32) for shape in ((B, T, H1), (B, T, 4 * H1), (B, T, H1), (B, 15, T), (B, T, 15), (B, T, 6), (B, T, H2), (B, T, 4 * H2), (B, T, H2))]
+wsf = torch.empty(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+_lib.check(lib.opn_opnet_fwd(B, T, H1, H2, bx.data_ptr(), xp1.data_ptr(), *[x.data_ptr() for x in w], *[o.data_ptr() for o in outs], wsf.data_ptr(), wsf.numel(), torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+print("done fused")

@@ -15,10 +15,11 @@ for r in rows[start + 2:]:
     except ValueError:
         pass
 short = lambda n: n.replace('void ', '').replace('opn::<unnamed>::', '').replace('(int)', '').replace('(bool)', '')
-# a step starts with the first recurrence forward launch of LSTM1 (H=256)
-idx = [i for i, (n, v) in enumerate(seq) if 'lstm_fwd' in n and '256' in short(n)[:40]]
-if len(idx) < 2:
-    idx = [i for i, (n, v) in enumerate(seq) if 'lstm_fwd' in n][::2]
+# one step = the launches between two consecutive fused forward kernels (cyclic: the x-projection contraction in
+# front of the kernel is counted at the end); without the fused forward, between two LSTM1 forward recurrences
+idx = [i for i, (n, v) in enumerate(seq) if 'opnet_fwd_fused' in n]
+if len(idx) < 3:
+    idx = [i for i, (n, v) in enumerate(seq) if 'lstm_fwd' in n and '256' in short(n)[:40]]
 a, b = idx[1], idx[2]
 tot = sum(v for _, v in seq[a:b])
 for n, v in seq[a:b]:
