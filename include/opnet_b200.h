@@ -159,6 +159,23 @@ OPN_API int opn_add(int64_t n, const float* a, const float* b, float* out, void*
 OPN_API int opn_loss_fwd_bwd(int64_t B, int64_t T, const float* y, const float* labels, const uint8_t* mask, int consistency,
                      float* loss_out, float* dy, void* stream);
 
+/* ---- optimiser step (baselines/training_main.py:150,217) ---------------------------
+ * torch.optim.Adam (amsgrad off) over one flat fp32 buffer of n parameters, in place:
+ *   g' = g + weight_decay * p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)         step = 1, 2, ...
+ * params / grads / exp_avg / exp_avg_sq: device pointers, 16-byte aligned, n floats each. */
+OPN_API int opn_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
+/* ---- IoU evaluation (baselines/training_main.py:97-112, baselines/tracking_utils.py:138-159) ----
+ * y, labels [N,T,4] normalised xyxy; pixels = int32(trunc(double(x) * [320,240,320,240])); per-frame IoU with the
+ * +1 pixel convention in double;  video_mean[n] = mean_t IoU  (ResultsAnalyzer "video_mean_iou");
+ * with mask (uint8 [N,T,4], a frame counts when any of its 4 entries is set, training_main.py:88):
+ * masked_mean[n] = mean over the masked frames (NaN when none; "containment_mean_iou"), masked_frames[n] their
+ * number.  frame_iou [N,T] (optional) receives the per-frame values.  masked_* / frame_iou may be NULL. */
+OPN_API int opn_iou_eval(int64_t N, int64_t T, const float* y, const float* labels, const uint8_t* mask, double* video_mean,
+                 double* masked_mean, int32_t* masked_frames, double* frame_iou, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

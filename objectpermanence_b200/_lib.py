@@ -42,6 +42,8 @@ SIGNATURES = {
     "opn_layernorm_bwd": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "opn_add": (c_int, [c_int64, _P, _P, _P, _P]),
     "opn_loss_fwd_bwd": (c_int, [c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P]),
+    "opn_adam_step": (c_int, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
+    "opn_iou_eval": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

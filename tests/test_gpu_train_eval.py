@@ -1,0 +1,138 @@
+"""GPU parity of the pieces right behind the hot path: the fused Adam step against torch.optim.Adam (the
+reference's optimiser, baselines/training_main.py:150) and the device IoU evaluation against the reference's own
+ResultsAnalyzer numbers (tests/golden/iou_metric.npz) and the numpy restatement in oracle/."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from objectpermanence_b200 import _lib
+from objectpermanence_b200.evaluation import inference_and_iou_comp, iou_eval
+from objectpermanence_b200.models_factory import ModelsFactory
+from objectpermanence_b200.optim import FusedAdam
+from objectpermanence_b200.synthetic import make_batch
+from oracle import opnet_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("n", [1, 5, 1024, 1000003])
+def test_adam_kernel_matches_torch_adam(cuda_device, n):
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8)
+    lib = _lib.load()
+    n_pad = (n + 3) // 4 * 4
+    p = torch.zeros(n_pad, device=cuda_device); p[:n] = p0.to(cuda_device)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 8):
+        grad = torch.randn(n, generator=g) * (10.0 ** (step % 3 - 1))
+        ref.grad = grad.double()
+        opt.step()
+        gd = torch.zeros(n_pad, device=cuda_device); gd[:n] = grad.to(cuda_device)
+        _lib.check(lib.opn_adam_step(n, p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), 3e-3, 0.9, 0.999, 1e-8, 0.0,
+                                     step, torch.cuda.current_stream().cuda_stream))
+        err = (p[:n].cpu().double() - ref.detach()).abs().max().item()
+        assert err <= 2e-6 * max(1.0, ref.detach().abs().max().item()), (step, err)
+
+
+def test_fused_adam_trains_like_torch_adam(cuda_device):
+    """Five optimiser steps of OPNet [4,16] with FusedAdam against torch.optim.Adam on an identical copy; also with
+    the gradients living in one flat buffer (the data-parallel reducer's layout)."""
+    from objectpermanence_b200.data_parallel import FlatGradAllReducer
+    from objectpermanence_b200.training import TrainingStep
+    cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    torch.manual_seed(0)
+    a = ModelsFactory.get_model("opnet", cfg).to(cuda_device)
+    b = ModelsFactory.get_model("opnet", cfg).to(cuda_device)
+    c = ModelsFactory.get_model("opnet", cfg).to(cuda_device)
+    b.load_state_dict(a.state_dict()); c.load_state_dict(a.state_dict())
+    steps = [TrainingStep(a, "opnet", optimizer=torch.optim.Adam(a.parameters(), lr=1e-3)),
+             TrainingStep(b, "opnet", optimizer=FusedAdam(b.parameters(), lr=1e-3)),
+             TrainingStep(c, "opnet", optimizer=FusedAdam(c.parameters(), lr=1e-3), reducer=FlatGradAllReducer(c.parameters()))]
+    for it in range(5):
+        boxes, labels, _ = make_batch(4, 16, 6, seed=50 + it)
+        boxes, labels = torch.from_numpy(boxes).to(cuda_device), torch.from_numpy(labels).to(cuda_device)
+        losses = [s.forward_backward(boxes, labels)[0].item() for s in steps]
+        assert abs(losses[0] - losses[1]) <= 1e-5 and abs(losses[0] - losses[2]) <= 1e-5, (it, losses)
+    for (k, pa), pb, pc in zip(a.state_dict().items(), b.state_dict().values(), c.state_dict().values()):
+        tol = 2e-5 * max(1.0, pa.abs().max().item())
+        assert (pa - pb).abs().max().item() <= tol and (pa - pc).abs().max().item() <= tol, k
+    # the model's state dict still loads into a fresh module (parameters are views of the flat buffer)
+    d = ModelsFactory.get_model("opnet", cfg)
+    d.load_state_dict({k: v.cpu() for k, v in b.state_dict().items()})
+
+
+def test_iou_eval_matches_reference_analyzer_fixture(cuda_device):
+    blob = np.load(f"{GOLDEN}/iou_metric.npz")
+    video, _, _, frame = iou_eval(torch.from_numpy(blob["pred"]).to(cuda_device), torch.from_numpy(blob["gt"]).to(cuda_device),
+                                  per_frame=True)
+    video = video.cpu().numpy()
+    assert np.abs(video - blob["per_video"]).max() <= 1e-12
+    assert abs(float(np.mean(video)) - float(blob["mean_iou"])) <= 1e-12
+    # per-frame values are bit-identical to the numpy restatement (integer arithmetic + one double division)
+    shape = oracle.FRAME_SHAPE
+    for n in range(blob["pred"].shape[0]):
+        want = oracle.video_iou((blob["pred"][n] * shape).astype(np.int32), (blob["gt"][n] * shape).astype(np.int32))
+        assert np.array_equal(frame[n].cpu().numpy(), want, equal_nan=True)
+
+
+def test_iou_eval_masked_frames_and_degenerate_boxes(cuda_device):
+    rng = np.random.default_rng(3)
+    N, T = 37, 300
+    y = rng.uniform(-0.2, 1.2, size=(N, T, 4)).astype(np.float32)       # includes x2 < x1 and out-of-frame boxes
+    labels = np.sort(rng.uniform(0, 1, size=(N, T, 2, 2)), axis=2).transpose(0, 1, 3, 2).reshape(N, T, 4).astype(np.float32)
+    labels = labels[..., [0, 2, 1, 3]]
+    mask = np.repeat(rng.uniform(size=(N, T, 1)) < 0.2, 4, axis=-1)
+    mask[5] = False                                                      # a video without containment frames -> NaN
+    y[7, 3] = labels[7, 3] = 0.0                                        # identical degenerate boxes
+    video, masked, frames, frame = iou_eval(torch.from_numpy(y).to(cuda_device), torch.from_numpy(labels).to(cuda_device),
+                                            torch.from_numpy(mask).to(cuda_device), per_frame=True)
+    shape = oracle.FRAME_SHAPE
+    for n in range(N):
+        want = oracle.video_iou((y[n] * shape).astype(np.int32), (labels[n] * shape).astype(np.int32))
+        got = frame[n].cpu().numpy()
+        assert np.array_equal(got, want, equal_nan=True)
+        assert np.isclose(video[n].item(), np.mean(want), rtol=1e-13, atol=0, equal_nan=True)
+        sel = mask[n].any(-1)
+        assert frames[n].item() == int(sel.sum())
+        if sel.sum() == 0:
+            assert math.isnan(masked[n].item())
+        else:
+            assert np.isclose(masked[n].item(), np.mean(want[sel]), rtol=1e-13, atol=0, equal_nan=True)
+
+
+def test_inference_and_iou_comp_mirrors_reference_loop(cuda_device):
+    """The evaluation pass over a loader that yields the reference's sample structure
+    ((boxes, index_to_track), (labels, mask), names): loss, mean IoU and containment IoU against the oracle."""
+    cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    params = oracle.init_params("opnet", cfg, seed=4)
+    model = ModelsFactory.get_model("opnet", cfg)
+    model.load_state_dict(params)
+    batches = []
+    for i in range(3):
+        boxes, labels, mask = make_batch(5, 300, 6, seed=700 + i)
+        batches.append(((torch.from_numpy(boxes), torch.zeros(5, 300, dtype=torch.int64)),
+                        (torch.from_numpy(labels), torch.from_numpy(mask)), [f"v{i}_{j}" for j in range(5)]))
+    avg_loss, miou, ciou = inference_and_iou_comp("opnet", model, cuda_device, batches, 15)
+    ys, ls, ms, losses = [], [], [], []
+    for (boxes, _), (labels, mask), _ in batches:
+        y_ref, _ = oracle.opnet_forward(params, boxes, fast=True)
+        ys.append(y_ref.numpy()); ls.append(labels.numpy()); ms.append(mask.numpy())
+        losses.append(float((y_ref - labels).abs().mean()) * 5)
+    y, labels, mask = np.concatenate(ys), np.concatenate(ls), np.concatenate(ms)
+    assert abs(avg_loss - sum(losses) / 15) <= 1e-5
+    assert round(miou, 3) == round(oracle.mean_iou(y, labels), 3)
+    shape = oracle.FRAME_SHAPE
+    per_video = []
+    for n in range(15):
+        iou = oracle.video_iou((y[n] * shape).astype(np.int32), (labels[n] * shape).astype(np.int32))
+        sel = mask[n].any(-1)
+        if sel.any():
+            per_video.append(float(np.mean(iou[sel])))
+    if per_video:
+        assert abs(ciou - float(np.mean(per_video))) <= 2e-3

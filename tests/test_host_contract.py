@@ -109,3 +109,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_fused_adam_and_iou_eval_have_no_cpu_path():
+    import torch
+    from objectpermanence_b200.evaluation import iou_eval
+    from objectpermanence_b200.optim import FusedAdam
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FusedAdam([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        iou_eval(torch.zeros(1, 2, 4), torch.zeros(1, 2, 4))
