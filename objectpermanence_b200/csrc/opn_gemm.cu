@@ -19,6 +19,10 @@ int gemm_tc(int trans_a, int trans_b, long long M, long long N, long long K, flo
             const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int relu,
             void* workspace, long long workspace_bytes, cudaStream_t s);
 
+// skinny shapes (opn_gemm_skinny.cu)
+int gemm_skinny(bool ta, bool tb, long long M, long long N, long long K, float alpha, const float* A, long long lda,
+                const float* B, long long ldb, float beta, float* C, long long ldc, cudaStream_t s, bool* handled);
+
 namespace {
 
 constexpr int BM = 128;
@@ -233,6 +237,11 @@ extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t
     OPN_CHECK_ARG(beta == 0.0f || beta == 1.0f, "sgemm: beta must be 0 or 1");
     const bool ta = trans_a != 0, tb = trans_b != 0;
     cudaStream_t s = as_stream(stream);
+    if (K > 0 && bias == nullptr && !relu) {
+        bool handled = false;
+        const int rc = gemm_skinny(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, s, &handled);
+        if (handled || rc != OPN_OK) return rc;
+    }
     if (K > 0 && workspace != nullptr && tc_eligible(M, N, K) &&
         workspace_bytes >= (int64_t)gemm_tc_workspace_bytes(M, N, K))
         return gemm_tc(trans_a, trans_b, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, relu, workspace,

@@ -103,6 +103,39 @@ def test_sgemm_tensor_core_epilogue(cuda_device):
     assert (big[:, N:] == 7.0).all()
 
 
+# ---- skinny contractions (rowdot / colred / tinyk fast paths and their fall-backs) ---------------------------
+@pytest.mark.parametrize("case", [
+    # (ta, tb, M, N, K, lda_pad, ldb_pad, ldc_pad, alpha, beta)
+    (False, True, 9600, 4, 512, 0, 0, 0, 1.0, 0.0),       # y = h2 Wo^T                      (rowdot)
+    (False, False, 9600, 6, 2048, 0, 0, 0, 1.0, 0.0),     # d frames_boxes = dgates2 W_ih2   (rowdot)
+    (False, False, 1000, 8, 256, 4, 2, 3, 0.5, 1.0),      # rowdot with padded rows, alpha, beta = 1
+    (False, False, 1000, 3, 250, 0, 0, 0, 1.0, 0.0),      # K % 4 != 0 -> tiled kernel
+    (False, False, 9600, 512, 4, 0, 0, 0, 1.0, 0.0),      # dh2 = dy Wo                       (tinyk)
+    (False, True, 9600, 2048, 6, 0, 0, 0, 1.0, 0.0),      # xproj2 = frames_boxes W_ih2^T     (tinyk)
+    (False, False, 700, 128, 7, 1, 4, 4, 2.0, 1.0),       # tinyk with strides, alpha, beta = 1
+    (True, False, 4, 512, 9600, 0, 0, 0, 1.0, 0.0),       # dWo = dy^T h2                     (colred, M skinny)
+    (True, False, 2048, 6, 9600, 0, 0, 0, 1.0, 0.0),      # dW_ih2 = dgates2^T frames_boxes   (colred, N skinny)
+    (True, False, 256, 15, 9600, 0, 0, 0, 1.0, 0.0),      # dW_pred^T = hs1^T dlogits         (colred)
+    (True, False, 300, 16, 1100, 3, 2, 5, -1.0, 1.0),     # colred with strides, alpha, beta = 1
+])
+def test_sgemm_skinny_shapes(cuda_device, case):
+    ta, tb, M, N, K, pa, pb, pc, alpha, beta = case
+    a_shape = (K, M) if ta else (M, K)
+    b_shape = (N, K) if tb else (K, N)
+    A = torch.zeros(a_shape[0], a_shape[1] + pa); A[:, :a_shape[1]] = _rand(a_shape, 11, 1.0)
+    Bm = torch.zeros(b_shape[0], b_shape[1] + pb); Bm[:, :b_shape[1]] = _rand(b_shape, 12, 1.0)
+    C0 = torch.zeros(M, N + pc); C0[:, :N] = _rand((M, N), 13, 1.0); C0[:, N:] = 7.0
+    opA = A[:, :a_shape[1]].double().t() if ta else A[:, :a_shape[1]].double()
+    opB = Bm[:, :b_shape[1]].double().t() if tb else Bm[:, :b_shape[1]].double()
+    want = alpha * (opA @ opB) + beta * C0[:, :N].double()
+    Cd = C0.to(cuda_device)
+    ops.sgemm(A.to(cuda_device), Bm.to(cuda_device), Cd, trans_a=ta, trans_b=tb, M=M, N=N, K=K, lda=A.shape[1],
+              ldb=Bm.shape[1], ldc=C0.shape[1], alpha=alpha, beta=beta)
+    got = Cd.cpu()
+    assert (got[:, :N].double() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+    assert (got[:, N:] == 7.0).all()
+
+
 # ---- persistent LSTM ------------------------------------------------------------------------
 def _lstm_case(B, T, I, H, seed, scale=1.0):
     x = _rand((B, T, I), seed, 1.0)
