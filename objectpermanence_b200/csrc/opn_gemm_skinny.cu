@@ -27,9 +27,10 @@ __global__ void __launch_bounds__(kSkinnyThreads) rowdot_kernel(const float* __r
                                                                 float* __restrict__ C, long long ldc, int M, int K,
                                                                 float alpha, int beta_one) {
     extern __shared__ __align__(16) float bs[];   // [N][K]
-    for (int i = threadIdx.x; i < N * K; i += kSkinnyThreads) {
-        const int n = i / K, k = i % K;
-        bs[i] = tb ? B[(long long)n * ldb + k] : B[(long long)k * ldb + n];
+    if (tb) {   // B[n][k]: rows of K contiguous floats
+        for (int i = threadIdx.x; i < N * K; i += kSkinnyThreads) bs[i] = B[(long long)(i / K) * ldb + i % K];
+    } else {    // B[k][n]: read along the (short) rows, scatter into [n][K]
+        for (int i = threadIdx.x; i < N * K; i += kSkinnyThreads) bs[(i % N) * K + i / N] = B[(long long)(i / N) * ldb + i % N];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(kSkinnyThreads) rowdot_kernel(const float* __r
         float acc[N];
 #pragma unroll
         for (int n = 0; n < N; ++n) acc[n] = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
         for (int k4 = lane; k4 < K / 4; k4 += 32) {
             const float4 a = __ldg(a4 + k4);
 #pragma unroll
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(kSkinnyThreads) rowdot_kernel(const float* __r
 }
 
 // ---- colred ----------------------------------------------------------------------------------------------------
-// C[w, j] += alpha * sum_{k in chunk} S[k][w] * L[k][j];  element (w, j) of C at C[w*cs_w + j*cs_j]
+// C[w, j] += alpha * sum_{k in chunk} S[k][w] * L[k][j];  element (w, j) of C at C[w*cs_w + j*cs_j].
+// Every thread owns 4 consecutive columns j (one 16-byte load per row of L) and 4*W accumulators.
 template <int W>
 __global__ void __launch_bounds__(kSkinnyThreads) colred_kernel(const float* __restrict__ S, long long lds,
                                                                 const float* __restrict__ L, long long ldl,
@@ -72,11 +74,11 @@ __global__ void __launch_bounds__(kSkinnyThreads) colred_kernel(const float* __r
                                                                 int J, int K, int k_per_cta, float alpha) {
     constexpr int KC = 64;                         // rows of S staged per pass
     __shared__ float ss[KC][W];
-    const int j = blockIdx.x * kSkinnyThreads + threadIdx.x;
+    const int j = 4 * (blockIdx.x * kSkinnyThreads + threadIdx.x);
     const int k_begin = blockIdx.y * k_per_cta, k_end = min(K, k_begin + k_per_cta);
-    float acc[W];
+    float acc[W][4];
 #pragma unroll
-    for (int w = 0; w < W; ++w) acc[w] = 0.0f;
+    for (int w = 0; w < W; ++w) acc[w][0] = acc[w][1] = acc[w][2] = acc[w][3] = 0.0f;
     for (int k0 = k_begin; k0 < k_end; k0 += KC) {
         const int kc = min(KC, k_end - k0);
         __syncthreads();
@@ -86,22 +88,38 @@ __global__ void __launch_bounds__(kSkinnyThreads) colred_kernel(const float* __r
             const float* lp = L + (long long)k0 * ldl + j;
             int kk = 0;
             for (; kk + 4 <= kc; kk += 4) {   // four rows in flight
-                const float l0 = __ldg(lp + (long long)(kk + 0) * ldl), l1 = __ldg(lp + (long long)(kk + 1) * ldl);
-                const float l2 = __ldg(lp + (long long)(kk + 2) * ldl), l3 = __ldg(lp + (long long)(kk + 3) * ldl);
+                float4 l[4];
 #pragma unroll
-                for (int w = 0; w < W; ++w)
-                    acc[w] = fmaf(l3, ss[kk + 3][w], fmaf(l2, ss[kk + 2][w], fmaf(l1, ss[kk + 1][w], fmaf(l0, ss[kk][w], acc[w]))));
+                for (int u = 0; u < 4; ++u) l[u] = __ldg(reinterpret_cast<const float4*>(lp + (long long)(kk + u) * ldl));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const float sv = ss[kk + u][w];
+                        acc[w][0] = fmaf(l[u].x, sv, acc[w][0]);
+                        acc[w][1] = fmaf(l[u].y, sv, acc[w][1]);
+                        acc[w][2] = fmaf(l[u].z, sv, acc[w][2]);
+                        acc[w][3] = fmaf(l[u].w, sv, acc[w][3]);
+                    }
             }
             for (; kk < kc; ++kk) {
-                const float l0 = __ldg(lp + (long long)kk * ldl);
+                const float4 l0 = __ldg(reinterpret_cast<const float4*>(lp + (long long)kk * ldl));
 #pragma unroll
-                for (int w = 0; w < W; ++w) acc[w] = fmaf(l0, ss[kk][w], acc[w]);
+                for (int w = 0; w < W; ++w) {
+                    const float sv = ss[kk][w];
+                    acc[w][0] = fmaf(l0.x, sv, acc[w][0]);
+                    acc[w][1] = fmaf(l0.y, sv, acc[w][1]);
+                    acc[w][2] = fmaf(l0.z, sv, acc[w][2]);
+                    acc[w][3] = fmaf(l0.w, sv, acc[w][3]);
+                }
             }
         }
     }
     if (j < J) {
 #pragma unroll
-        for (int w = 0; w < W; ++w) atomicAdd(C + w * cs_w + j * cs_j, alpha * acc[w]);
+        for (int w = 0; w < W; ++w)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(C + w * cs_w + (j + c) * cs_j, alpha * acc[w][c]);
     }
 }
 
@@ -158,7 +176,7 @@ int launch_rowdot(const float* A, long long lda, const float* B, long long ldb, 
     const size_t smem = (size_t)N * K * sizeof(float);
     OPN_CUDA(cudaFuncSetAttribute(rowdot_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (M + 7) / 8;
-    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid > 148 * 2) grid = 148 * 2;   // the staging of B (up to 48 KB per CTA) is amortised over ~32 rows
     rowdot_kernel<N><<<(unsigned)grid, kSkinnyThreads, smem, s>>>(A, lda, B, ldb, tb, C, ldc, M, K, alpha, beta_one);
     OPN_CUDA(cudaGetLastError());
     count_launch();
@@ -174,8 +192,8 @@ int launch_colred(const float* S, long long lds, const float* L, long long ldl, 
         OPN_CUDA(cudaGetLastError());
         count_launch();
     }
-    const int gx = (J + kSkinnyThreads - 1) / kSkinnyThreads;
-    int splits = (148 * 4 + gx - 1) / gx;                 // about four CTAs per SM in total
+    const int gx = (J / 4 + kSkinnyThreads - 1) / kSkinnyThreads;
+    int splits = (148 * 2 + gx - 1) / gx;                 // about two CTAs per SM in total
     int k_per_cta = (K + splits - 1) / splits;
     k_per_cta = (k_per_cta + 63) / 64 * 64;
     if (k_per_cta < 64) k_per_cta = 64;
@@ -234,7 +252,7 @@ int gemm_skinny(bool ta, bool tb, long long M, long long N, long long K, float a
     }
     // colred: C = A^T B over a long K with one side at most 16 wide
     if (ta && !tb && K >= 1024) {
-        if (N <= 16 && M >= 64) {          // skinny operand = B [K x N], large = A [K x M]; C[m][n]: w = n, j = m
+        if (N <= 16 && M >= 512 && M % 4 == 0 && lda % 4 == 0 && aligned16(A)) {   // skinny = B [K x N], large = A [K x M]; w = n, j = m
             *handled = true;
             switch ((int)N) {
 #define OPN_CASE(w) case w: return launch_colred<w>(B, ldb, A, lda, C, 1, ldc, (int)M, (int)K, alpha, beta_one, s);
@@ -243,7 +261,7 @@ int gemm_skinny(bool ta, bool tb, long long M, long long N, long long K, float a
 #undef OPN_CASE
             }
         }
-        if (M <= 16 && N >= 64) {          // skinny operand = A [K x M], large = B [K x N]; C[m][n]: w = m, j = n
+        if (M <= 16 && N >= 512 && N % 4 == 0 && ldb % 4 == 0 && aligned16(B)) {   // skinny = A [K x M], large = B [K x N]; w = m, j = n
             *handled = true;
             switch ((int)M) {
 #define OPN_CASE(w) case w: return launch_colred<w>(A, lda, B, ldb, C, ldc, 1, (int)N, (int)K, alpha, beta_one, s);
