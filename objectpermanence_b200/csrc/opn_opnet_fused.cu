@@ -427,7 +427,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
         }
         __syncthreads();
         // h2[i-2] was published a whole LSTM1 phase ago: stream it in while the cells / the head are computed.
-        // (Issued one phase earlier, before the LSTM1 MMAs, 10 % of the sweeps came back stale: 1.04 ms against 1.00.)
+        // (Issued one phase earlier, before the LSTM1 MMAs, 10 % of the sweeps came back stale: 1.04 ms against 1.00.
+        // Gating the early issue on a canary -- warp 0 samples the last word of each producer with a polling load a
+        // phase ahead -- removed the stale sweeps but ran at 1.35 ms: the extra loads on the lines being written cost
+        // more than the wait they save.)
         if (i >= 2) issue_sweep<KS2 * 32 * 16>(sw2, bars2, land2_s, ring2 + (size_t)((i - 2) & 1) * (kGroup * H2), crank);
         PH(3);  // LSTM1 + head MMAs + barrier
         if (warp < 4) {
