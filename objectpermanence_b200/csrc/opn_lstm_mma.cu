@@ -508,12 +508,22 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
 bool lstm_mma_supported(int64_t H) { return H == 256 || H == 512; }
 
 int lstm_fwd_mma(const FwdParams& p, int64_t B, int64_t H, cudaStream_t s) {
-    if (H == 256) return launch_ring(lstm_fwd_mma_kernel<256, 1>, p, kThreads, 32, 0, B, s, "lstm_fwd");
+    if (H == 256) {
+        const char* e = getenv("OPN_LSTM_FWD256_RG");
+        if (e && e[0] == '2') return launch_ring(lstm_fwd_mma_kernel<256, 2>, p, 2 * kThreads, 16, 0, B, s, "lstm_fwd");
+        return launch_ring(lstm_fwd_mma_kernel<256, 1>, p, kThreads, 32, 0, B, s, "lstm_fwd");
+    }
     return launch_ring(lstm_fwd_mma_kernel<512, 2>, p, 2 * kThreads, 32, 0, B, s, "lstm_fwd");
 }
 
 int lstm_bwd_mma(const BwdParams& p, int64_t B, int64_t H, cudaStream_t s) {
-    if (H == 256) return launch_ring(lstm_bwd_mma_kernel<256, 1>, p, kThreads, 32, 0, B, s, "lstm_bwd");
+    if (H == 256) {
+        // 16-unit CTAs: 16 producers per batch group instead of 32 halve the reduce-scatter traffic (every producer sends
+        // a partial [8, H] whatever its size): 1.92 against 2.31 us/step.  OPN_LSTM_BWD256_RG=1 selects 8-unit CTAs.
+        const char* e = getenv("OPN_LSTM_BWD256_RG");
+        if (e && e[0] == '1') return launch_ring(lstm_bwd_mma_kernel<256, 1>, p, kThreads, 32, 0, B, s, "lstm_bwd");
+        return launch_ring(lstm_bwd_mma_kernel<256, 2>, p, 2 * kThreads, 16, 0, B, s, "lstm_bwd");
+    }
     return launch_ring(lstm_bwd_mma_kernel<512, 2>, p, 2 * kThreads, 32, 0, B, s, "lstm_bwd");
 }
 
