@@ -288,9 +288,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long rows, int 
 }
 
 // ---- fused training loss ---------------------------------------------------------------
-// One CTA (deterministic reduction).  out[0] = total, out[1] = prediction term, out[2] =
-// consistency term (always reported, added to the total only when `consistency` != 0).
-__global__ void __launch_bounds__(1024) loss_kernel(int B, int T, const float* __restrict__ y,
+// out[0] = total, out[1] = prediction term, out[2] = consistency term (always reported, added to the
+// total only when `consistency` != 0).  Every term is linear in the per-row sums, so the CTAs add their
+// share to the zeroed 3-vector with fp32 atomics (dy, the gradient, does not depend on the reduction).
+__global__ void __launch_bounds__(256) loss_kernel(int B, int T, const float* __restrict__ y,
                                                     const float* __restrict__ labels,
                                                     const uint8_t* __restrict__ mask, int consistency,
                                                     float* __restrict__ out, float* __restrict__ dy) {
@@ -301,7 +302,8 @@ __global__ void __launch_bounds__(1024) loss_kernel(int B, int T, const float* _
     const float w_cons = (consistency && pairs > 0) ? 0.5f / (float)pairs : 0.0f;
     float pred = 0.0f, cons = 0.0f;
     // one thread per (video, frame): 4 coordinates
-    for (long long r = threadIdx.x; r < (long long)B * T; r += blockDim.x) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < (long long)B * T;
+         r += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(r % T);
         const float4 yv = *reinterpret_cast<const float4*>(y + r * 4);
         const float4 lv = *reinterpret_cast<const float4*>(labels + r * 4);
@@ -342,9 +344,9 @@ __global__ void __launch_bounds__(1024) loss_kernel(int B, int T, const float* _
     if (threadIdx.x == 0) {
         const float pred_mean = pred * w_pred;
         const float cons_mean = pairs > 0 ? cons / (float)pairs : 0.0f;
-        out[1] = pred_mean;
-        out[2] = cons_mean;
-        out[0] = consistency ? pred_mean + 0.5f * cons_mean : pred_mean;
+        atomicAdd(out + 1, pred_mean);
+        atomicAdd(out + 2, cons_mean);
+        atomicAdd(out + 0, consistency ? pred_mean + 0.5f * cons_mean : pred_mean);
     }
 }
 
@@ -470,7 +472,10 @@ extern "C" int opn_layernorm_bwd(int64_t rows, int64_t D, const float* xhat, con
 extern "C" int opn_loss_fwd_bwd(int64_t B, int64_t T, const float* y, const float* labels, const uint8_t* mask,
                                 int consistency, float* loss_out, float* dy, void* stream) {
     OPN_CHECK_ARG(B > 0 && T > 0 && y && labels && loss_out && dy, "loss_fwd_bwd: bad argument");
-    loss_kernel<<<1, 1024, 0, as_stream(stream)>>>((int)B, (int)T, y, labels, mask, consistency, loss_out, dy);
+    OPN_CUDA(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), as_stream(stream)));
+    long long blocks = (B * T + 255) / 256;
+    if (blocks > 148) blocks = 148;
+    loss_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((int)B, (int)T, y, labels, mask, consistency, loss_out, dy);
     OPN_CUDA(cudaGetLastError());
     count_launch();
     return OPN_OK;
