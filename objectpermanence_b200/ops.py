@@ -192,27 +192,30 @@ class LstmLayerFn(torch.autograd.Function):
         return _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, ctx.needs_input_grad)
 
 
-def _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, needs):
-    """Reverse recurrence + the three time-parallel contractions of one LSTM layer -> (dx, dW_ih, dW_hh)."""
-    B, T, I = x.shape
-    H = w_hh.shape[1]
+def _lstm_recurrence_backward(w_hh, gates, cells, dhs):
+    """Reverse recurrence of one LSTM layer -> dgates [B,T,4H] = dLoss / d(pre-activation gates)."""
+    B, T, H4 = gates.shape
+    H = H4 // 4
     lib = _lib.load()
-    dev = x.device
     dhs = dhs.contiguous()
-    dgates = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
-    ws = _lstm_workspace(B, T, H, dev)
+    dgates = torch.empty(B, T, 4 * H, device=gates.device, dtype=torch.float32)
+    ws = _lstm_workspace(B, T, H, gates.device)
     rc = lib.opn_lstm_bwd(B, T, H, w_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dhs.data_ptr(),
                           dgates.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "opn_lstm_bwd")
     _lstm_check(ws, "opn_lstm_bwd")
-    dx = dw_ih = dw_hh = None
-    if needs[0]:
-        dx = torch.empty_like(x)
-        sgemm(dgates, w_ih, dx, trans_a=False, trans_b=False, M=B * T, N=I, K=4 * H, lda=4 * H, ldb=I, ldc=I)
-    if needs[1]:
+    return dgates
+
+
+def _lstm_weight_grads(dgates, x, hs, w_ih, w_hh, need_dw_ih, need_dw_hh):
+    """The two time-parallel weight-gradient contractions of one LSTM layer -> (dW_ih, dW_hh)."""
+    B, T, I = x.shape
+    H = w_hh.shape[1]
+    dw_ih = dw_hh = None
+    if need_dw_ih:
         dw_ih = torch.empty_like(w_ih)
         sgemm(dgates, x, dw_ih, trans_a=True, trans_b=False, M=4 * H, N=I, K=B * T, lda=4 * H, ldb=I, ldc=I)
-    if needs[2]:
+    if need_dw_hh:
         dw_hh = torch.empty_like(w_hh)
         if T > 1:
             # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1].  Contract the flat row pairs (r+1, r) over all
@@ -224,7 +227,31 @@ def _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, needs):
                       ldb=T * H, ldc=H, alpha=-1.0, beta=1.0, a_off=T * 4 * H, b_off=(T - 1) * H)
         else:
             dw_hh.zero_()
+    return dw_ih, dw_hh
+
+
+def _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, needs):
+    """Reverse recurrence + the three time-parallel contractions of one LSTM layer -> (dx, dW_ih, dW_hh)."""
+    B, T, I = x.shape
+    H = w_hh.shape[1]
+    dgates = _lstm_recurrence_backward(w_hh, gates, cells, dhs)
+    dx = None
+    if needs[0]:
+        dx = torch.empty_like(x)
+        sgemm(dgates, w_ih, dx, trans_a=False, trans_b=False, M=B * T, N=I, K=4 * H, lda=4 * H, ldb=I, ldc=I)
+    dw_ih, dw_hh = _lstm_weight_grads(dgates, x, hs, w_ih, w_hh, needs[1], needs[2])
     return dx, dw_ih, dw_hh
+
+
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """One auxiliary stream per device for work that runs beside a recurrence kernel."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 class WhoToTrackFn(torch.autograd.Function):
@@ -258,8 +285,8 @@ class WhoToTrackFn(torch.autograd.Function):
         return None, dhs1, dw
 
 
-def _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, need_dw):
-    """who-to-track backward -> (d hs1, dW_pred)."""
+def _wtt_backward_kernel(boxes, hs1, w_pred, probs, dfb, dlogits):
+    """who-to-track backward -> (d hs1, d logits [B,T,15] in row layout)."""
     B, T, NO, F = boxes.shape
     H1 = hs1.shape[-1]
     dev = boxes.device
@@ -272,14 +299,22 @@ def _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, need_dw):
     rc = _lib.load().opn_wtt_bwd(B, T, H1, boxes.data_ptr(), probs.data_ptr(), w_pred.data_ptr(), dfb.data_ptr(),
                                  _ptr(dl_up), dl.data_ptr(), dhs1.data_ptr(), _stream())
     _lib.check(rc, "opn_wtt_bwd")
-    dw = None
-    if need_dw:
-        # dW_pred^T [H1,15] = hs1^T dl: contracted in the transposed orientation so that the long dimension
-        # (H1) maps to the 128-row tile and the 15 objects to the 16-wide one (as M=15 it ran 7x slower)
-        dw_t = torch.empty(H1, 15, device=dev, dtype=torch.float32)
-        sgemm(hs1, dl, dw_t, trans_a=True, trans_b=False, M=H1, N=15, K=B * T, lda=H1, ldb=15, ldc=15)
-        dw = dw_t.t()
-    return dhs1, dw
+    return dhs1, dl
+
+
+def _wtt_weight_grad(hs1, dl):
+    """dW_pred^T [H1,15] = hs1^T dl: contracted in the transposed orientation so that the long dimension (H1) maps
+    to the 128-row tile and the 15 objects to the 16-wide one (as M=15 it ran 7x slower)."""
+    B, T, H1 = hs1.shape
+    dw_t = torch.empty(H1, 15, device=hs1.device, dtype=torch.float32)
+    sgemm(hs1, dl, dw_t, trans_a=True, trans_b=False, M=H1, N=15, K=B * T, lda=H1, ldb=15, ldc=15)
+    return dw_t.t()
+
+
+def _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, need_dw):
+    """who-to-track backward -> (d hs1, dW_pred)."""
+    dhs1, dl = _wtt_backward_kernel(boxes, hs1, w_pred, probs, dfb, dlogits)
+    return dhs1, (_wtt_weight_grad(hs1, dl) if need_dw else None)
 
 
 class OPNetTrunkFn(torch.autograd.Function):
@@ -334,10 +369,41 @@ class OPNetTrunkFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         if dhs2 is None:
             dhs2 = torch.zeros_like(hs2)
-        dfb, dw_ih2, dw_hh2 = _lstm_backward(fb, w_ih2, w_hh2, hs2, gates2, cells2, dhs2, (True, need[4], need[5]))
-        dhs1, dw_pred = _wtt_backward(boxes, hs1, w_pred, probs, dfb, dlogits, need[3])
+        H2 = w_hh2.shape[1]
+        dgates2 = _lstm_recurrence_backward(w_hh2, gates2, cells2, dhs2)
+        dfb = torch.empty_like(fb)
+        sgemm(dgates2, w_ih2, dfb, trans_a=False, trans_b=False, M=B * T, N=6, K=4 * H2, lda=4 * H2, ldb=6, ldc=6)
+        # The weight gradients of LSTM2 depend only on dgates2: they run on a side stream beside the who-to-track
+        # backward and the LSTM1 reverse recurrence, which occupies 64 of the 148 SMs (OPN_OPNET_OVERLAP=0: in line).
+        overlap = os.environ.get("OPN_OPNET_OVERLAP", "1") not in ("0", "") and (need[3] or need[4] or need[5])
+        if overlap:
+            main, side = torch.cuda.current_stream(), _side_stream(boxes.device)
+            ready = torch.cuda.Event()
+            ready.record(main)     # dgates2 and d frames_boxes are complete
+        dhs1, dl = _wtt_backward_kernel(boxes, hs1, w_pred, probs, dfb, dlogits)
+        if overlap:
+            ready_dl = torch.cuda.Event()
+            ready_dl.record(main)
         x1 = boxes.reshape(B, T, -1)
-        _, dw_ih1, dw_hh1 = _lstm_backward(x1, w_ih1, w_hh1, hs1, gates1, cells1, dhs1, (False, need[1], need[2]))
+        dgates1 = _lstm_recurrence_backward(w_hh1, gates1, cells1, dhs1)     # enqueued first: takes its 64 SMs
+        if overlap:
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, need[4], need[5])
+                side.wait_event(ready_dl)
+                dw_pred = _wtt_weight_grad(hs1, dl) if need[3] else None
+            for t_ in (dgates2, fb, hs2, hs1, dl):
+                t_.record_stream(side)
+            done = torch.cuda.Event()
+            done.record(side)
+            main.wait_event(done)
+            for t_ in (dw_ih2, dw_hh2, dw_pred):
+                if t_ is not None:
+                    t_.record_stream(main)
+        else:
+            dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, need[4], need[5])
+            dw_pred = _wtt_weight_grad(hs1, dl) if need[3] else None
+        dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, x1, hs1, w_ih1, w_hh1, need[1], need[2])
         return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
 
 
