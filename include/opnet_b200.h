@@ -176,6 +176,11 @@ OPN_API int opn_adam_step(int64_t n, float* params, const float* grads, float* e
 OPN_API int opn_iou_eval(int64_t N, int64_t T, const float* y, const float* labels, const uint8_t* mask, double* video_mean,
                  double* masked_mean, int32_t* masked_frames, double* frame_iou, void* stream);
 
+/* ---- pixel boxes (baselines/inference_main.py:214-215, baselines/training_main.py:98-101) ----
+ * pixels[r][c] = int32(trunc(double(boxes[r][c]) * {320,240,320,240}[c])) for rows normalised xyxy boxes: the
+ * `(np.array(predictions) * frame_shapes).astype(np.int32)` of the reference, on the device. */
+OPN_API int opn_to_pixels(int64_t rows, const float* boxes, int32_t* pixels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

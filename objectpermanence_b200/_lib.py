@@ -44,6 +44,7 @@ SIGNATURES = {
     "opn_loss_fwd_bwd": (c_int, [c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P]),
     "opn_adam_step": (c_int, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
     "opn_iou_eval": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "opn_to_pixels": (c_int, [c_int64, _P, _P, _P]),
 }
 
 _lib = None

@@ -144,3 +144,32 @@ extern "C" int opn_iou_eval(int64_t N, int64_t T, const float* y, const float* l
     count_launch();
     return OPN_OK;
 }
+
+// ---- pixel boxes for the inference writer (baselines/inference_main.py:214-215) -------------------------------
+namespace opn {
+namespace {
+__global__ void __launch_bounds__(256) to_pixels_kernel(long long rows, const float* __restrict__ x, int* __restrict__ out) {
+    const double shape[4] = {320.0, 240.0, 320.0, 240.0};
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * 4);
+        int4 o;
+        // numpy: float32 array * int64 array -> float64, .astype(np.int32) truncates toward zero
+        o.x = (int)((double)v.x * shape[0]);
+        o.y = (int)((double)v.y * shape[1]);
+        o.z = (int)((double)v.z * shape[2]);
+        o.w = (int)((double)v.w * shape[3]);
+        *reinterpret_cast<int4*>(out + r * 4) = o;
+    }
+}
+}  // namespace
+}  // namespace opn
+
+extern "C" int opn_to_pixels(int64_t rows, const float* boxes, int32_t* pixels, void* stream) {
+    OPN_CHECK_ARG(rows > 0 && boxes && pixels, "to_pixels: bad argument");
+    long long blocks = (rows + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    opn::to_pixels_kernel<<<(unsigned)blocks, 256, 0, opn::as_stream(stream)>>>((long long)rows, boxes, pixels);
+    OPN_CUDA(cudaGetLastError());
+    opn::count_launch();
+    return OPN_OK;
+}

@@ -136,3 +136,44 @@ def test_inference_and_iou_comp_mirrors_reference_loop(cuda_device):
             per_video.append(float(np.mean(iou[sel])))
     if per_video:
         assert abs(ciou - float(np.mean(per_video))) <= 2e-3
+
+
+def test_to_pixels_matches_numpy_semantics(cuda_device):
+    from objectpermanence_b200.inference import to_pixels
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1.5, 2.5, size=(5000, 4)).astype(np.float32)
+    x[:8] = [[0, 0, 0, 0], [1, 1, 1, 1], [-0.0031, 0.9999999, 0.5, 0.25], [1 / 320, 1 / 240, 319 / 320, 239 / 240],
+             [0.003124999, 0.004166666, 0.99687499, 0.99583333], [-1e-9, 1e-9, 1 - 1e-7, 1 + 1e-7], [7 / 320, 9 / 240, 11 / 320, 13 / 240],
+             [np.float32(0.1), np.float32(0.2), np.float32(0.3), np.float32(0.7)]]
+    want = (x * np.array([320, 240, 320, 240])).astype(np.int32)     # inference_main.py:214
+    got = to_pixels(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+
+
+def test_inference_pass_and_writer(cuda_device, tmp_path):
+    """predict_pixel_boxes / run_inference against the oracle forward + the reference's numpy post-processing, and
+    the JSON the reference's DataHelper.write_bb_predictions_to_file would leave."""
+    import json
+    from objectpermanence_b200.inference import predict_pixel_boxes, run_inference
+    cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    params = oracle.init_params("opnet", cfg, seed=9, scale=3.0)
+    model = ModelsFactory.get_model("opnet", cfg)
+    model.load_state_dict(params)
+    batches = []
+    for i in range(2):
+        boxes, labels, mask = make_batch(3, 300, 6, seed=900 + i)
+        batches.append(((torch.from_numpy(boxes), torch.zeros(3, 300, dtype=torch.int64)),
+                        (torch.from_numpy(labels), torch.from_numpy(mask)), [f"CATER_new_{i}{j}" for j in range(3)]))
+    indices, preds, labs = predict_pixel_boxes("opnet", model, cuda_device, batches)
+    shape = np.array([320, 240, 320, 240])
+    y_ref = np.concatenate([oracle.opnet_forward(params, b[0][0], fast=True)[0].numpy() for b in batches])
+    want_labels = (np.concatenate([b[1][0].numpy() for b in batches]).reshape(-1, 4) * shape).reshape(6, 300, 4).astype(np.int32)
+    want_preds = (y_ref.reshape(-1, 4) * shape).reshape(6, 300, 4).astype(np.int32)
+    assert np.array_equal(labs, want_labels)
+    assert np.abs(preds.astype(np.int64) - want_preds).max() <= 1          # a 1e-7 difference may flip one pixel
+    assert (preds != want_preds).mean() < 1e-3
+    assert indices == {f"CATER_new_{i}{j}": 3 * i + j for i in range(2) for j in range(3)}
+    files = run_inference("opnet", model, cuda_device, batches, str(tmp_path))
+    for name, row in indices.items():
+        expected = json.dumps([[int(v) for v in box] for box in preds[row]], indent=2)
+        assert files[name].name == name + "_bb.json" and files[name].read_text() == expected
