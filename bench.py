@@ -225,7 +225,15 @@ def run_ours(args):
     # (1) device-resident inputs
     total_ms, launches, w0, w1 = timed(lambda: step.forward_backward(boxes_d, labels_d), args.steps, args.warmup)
     # (2) end to end from pinned host buffers through the public step API
-    e2e_ms, _, _, w2 = timed(lambda: step(boxes_h, labels_h), args.steps, max(1, args.warmup // 2))
+    # The pipelined form of the public step: every step copies its inputs from pinned host memory (copy stream, double
+    # buffered) and reads its 12-byte loss vector back; the host waits for the loss of the PREVIOUS step, the last one is
+    # drained inside the timed region (the barrier + synchronize that closes it).  OPN_E2E_SYNC=1: the blocking form.
+    if os.environ.get("OPN_E2E_SYNC", "0") not in ("0", ""):
+        e2e_fn = lambda: step(boxes_h, labels_h)
+    else:
+        e2e_fn = lambda: step.pipelined(boxes_h, labels_h)
+    e2e_ms, _, _, w2 = timed(e2e_fn, args.steps, max(1, args.warmup // 2))
+    step.drain()
     clocks = sampler.stop(w0, w2) if sampler else None
 
     ms_per_step = total_ms / args.steps

@@ -6,6 +6,12 @@ with the model call, the loss and the backward on sm_100a kernels.
 
 The reference's three per-step `.item()` host syncs (training_main.py:212-214) are replaced by
 one 12-byte device->host read of the (total, prediction, consistency) vector.
+
+`step.pipelined(boxes, labels, mask)` is the asynchronous form ("async logging"): the inputs go to
+the device on a copy stream (double buffered, so the copy of step k+1 overlaps the kernels of step k), the loss
+vector of the step is copied to a pinned slot without waiting, and the call returns the loss of the PREVIOUS step
+(None on the first call); `step.drain()` returns the last one.  The host never waits for the step it has just
+enqueued, so the GPU queue stays full.
 """
 from __future__ import annotations
 
@@ -35,6 +41,11 @@ class TrainingStep:
         self.optimizer = optimizer
         self.device = next(model.parameters()).device
         self._loss_host = torch.empty(3, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
+        # pipelined form: two slots of (device input buffers, pinned loss vector, completion event)
+        self._slots = None
+        self._copy_stream = None
+        self._k = 0
+        self._pending = None
 
     def forward_backward(self, boxes: torch.Tensor, labels: torch.Tensor, mask: Optional[torch.Tensor] = None):
         """zero_grad + forward + loss + backward (+ gradient all-reduce).  Device tensors in, the
@@ -62,3 +73,55 @@ class TrainingStep:
         self._loss_host.copy_(loss3, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return tuple(float(v) for v in self._loss_host)
+
+    # ---- pipelined form -----------------------------------------------------------------------------------
+    def _slot(self, boxes, labels, mask):
+        if self._slots is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._slots = []
+            for _ in range(2):
+                self._slots.append({
+                    "boxes": torch.empty(boxes.shape, dtype=boxes.dtype, device=self.device),
+                    "labels": torch.empty(labels.shape, dtype=labels.dtype, device=self.device),
+                    "mask": torch.empty(mask.shape, dtype=mask.dtype, device=self.device) if mask is not None else None,
+                    "loss": torch.empty(3, dtype=torch.float32).pin_memory(),
+                    "copied": torch.cuda.Event(), "done": torch.cuda.Event(), "free": torch.cuda.Event(),
+                })
+        slot = self._slots[self._k & 1]
+        if slot["boxes"].shape != boxes.shape or slot["labels"].shape != labels.shape:
+            raise RuntimeError("pipelined steps need a fixed batch shape (use drop_last / the synchronous call for the tail)")
+        return slot
+
+    def pipelined(self, boxes: torch.Tensor, labels: torch.Tensor, mask: Optional[torch.Tensor] = None):
+        """Enqueue one step from pinned HOST tensors and return the loss triple of the previous step (None at first)."""
+        slot = self._slot(boxes, labels, mask)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            if self._k >= 2:
+                self._copy_stream.wait_event(slot["free"])      # the step that last read these buffers has finished
+            slot["boxes"].copy_(boxes, non_blocking=True)
+            slot["labels"].copy_(labels, non_blocking=True)
+            if mask is not None:
+                slot["mask"].copy_(mask, non_blocking=True)
+            slot["copied"].record(self._copy_stream)
+        main.wait_event(slot["copied"])
+        loss3 = self.forward_backward(slot["boxes"], slot["labels"], slot["mask"])
+        slot["free"].record(main)
+        slot["loss"].copy_(loss3, non_blocking=True)
+        slot["done"].record(main)
+        previous = self._pending
+        self._pending = slot
+        self._k += 1
+        if previous is None:
+            return None
+        previous["done"].synchronize()
+        return tuple(float(v) for v in previous["loss"])
+
+    def drain(self):
+        """Wait for the last pipelined step and return its loss triple."""
+        if self._pending is None:
+            return None
+        self._pending["done"].synchronize()
+        out = tuple(float(v) for v in self._pending["loss"])
+        self._pending = None
+        return out

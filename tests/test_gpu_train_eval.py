@@ -177,3 +177,29 @@ def test_inference_pass_and_writer(cuda_device, tmp_path):
     for name, row in indices.items():
         expected = json.dumps([[int(v) for v in box] for box in preds[row]], indent=2)
         assert files[name].name == name + "_bb.json" and files[name].read_text() == expected
+
+
+def test_pipelined_step_returns_lagged_losses(cuda_device):
+    """step.pipelined() (copy stream + double buffering + lagged loss read-back) against the blocking step() on an
+    identical model: same losses, one step late, and the same weights after the last optimiser step."""
+    from objectpermanence_b200.training import TrainingStep
+    cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    torch.manual_seed(1)
+    a = ModelsFactory.get_model("opnet", cfg).to(cuda_device)
+    b = ModelsFactory.get_model("opnet", cfg).to(cuda_device)
+    b.load_state_dict(a.state_dict())
+    sa = TrainingStep(a, "opnet", optimizer=FusedAdam(a.parameters(), lr=1e-3))
+    sb = TrainingStep(b, "opnet", optimizer=FusedAdam(b.parameters(), lr=1e-3))
+    batches = []
+    for it in range(5):
+        boxes, labels, _ = make_batch(4, 16, 6, seed=80 + it)
+        batches.append((torch.from_numpy(boxes).pin_memory(), torch.from_numpy(labels).pin_memory()))
+    blocking = [sa(bx, lb) for bx, lb in batches]
+    lagged = [sb.pipelined(bx, lb) for bx, lb in batches]
+    assert lagged[0] is None
+    got = lagged[1:] + [sb.drain()]
+    for want, have in zip(blocking, got):
+        assert all(abs(w - h) <= 1e-6 for w, h in zip(want, have)), (want, have)
+    assert sb.drain() is None
+    for (k, pa), pb in zip(a.state_dict().items(), b.state_dict().values()):
+        assert (pa - pb).abs().max().item() <= 1e-6 * max(1.0, pa.abs().max().item()), k
