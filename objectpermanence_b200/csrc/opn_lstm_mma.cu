@@ -373,6 +373,9 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
         const int buf = s & 1;
         PH(0);  // reduction of the gathered partials
         // ---- 1. cell backward for the CTA's own units ---------------------------------------------------
+        // Critical path first: d(pre-activation gates) -> scaled fp16 fragments in shared memory.  The exact copies
+        // to `dgates` and the stash prefetch are issued behind the barrier, in the shadow of the MMAs.
+        float v0 = 0.0f, v1 = 0.0f;
         if (valid) {
             const float dh = sdh + dh_rec;
             const float tc = tanh_sfu(sc);
@@ -382,18 +385,12 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
             const float d_g = dc * si;
             const float d_f = dc * scp;
             dc_carry = dc * sf;
-            float* dg = p.dgates + (row0 + t) * (size_t)(4 * H) + u;
-            float v0, v1;
             if (half == 0) {
                 v0 = d_i * si * (1.0f - si);
                 v1 = d_f * sf * (1.0f - sf);
-                dg[0] = v0;
-                dg[H] = v1;
             } else {
                 v0 = d_g * (1.0f - sg * sg);
                 v1 = d_o * so * (1.0f - so);
-                dg[2 * H] = v0;
-                dg[3 * H] = v1;
             }
             if (t > 0) {
                 // per-video power-of-two scale from the largest |da| of the CTA's cells of this video
@@ -407,20 +404,31 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
                 w[0] = hi;
                 w[2] = lo;
                 if (ul == 0 && half == 0) dainv_s[buf][bl] = inv2 * winv;
-                // rotate: step t-1 becomes current, issue the loads of step t-2
-                si = ni, sf = nf, sg = ng, so = no, sdh = ndh;
-                sc = scp;
-                scp = ncp;
-                if (t > 1) {
-                    load_next(t - 2);
-                    ncp = (t > 2) ? __ldg(p.cells + (row0 + t - 3) * H + u) : 0.0f;
-                }
             }
         }
-        if (t == 0) break;
+        auto store_dgates = [&]() {
+            float* dg = p.dgates + (row0 + t) * (size_t)(4 * H) + u + (half ? 2 * H : 0);
+            dg[0] = v0;
+            dg[H] = v1;
+        };
+        if (t == 0) {
+            if (valid) store_dgates();
+            break;
+        }
         PH(1);  // cell backward
         if (__syncthreads_or(my_abort)) break;  // dafrag_s[buf] complete (double buffered: one barrier per step)
         PH(2);  // barrier
+        if (valid) {
+            store_dgates();
+            // rotate: step t-1 becomes current, issue the loads of step t-2
+            si = ni, sf = nf, sg = ng, so = no, sdh = ndh;
+            sc = scp;
+            scp = ncp;
+            if (t > 1) {
+                load_next(t - 2);
+                ncp = (t > 2) ? __ldg(p.cells + (row0 + t - 3) * H + u) : 0.0f;
+            }
+        }
 
         // ---- 2. partial[k][b] over the own rows; publish ------------------------------------------------
         const uint32_t par = step_parity(s);
