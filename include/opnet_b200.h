@@ -132,6 +132,21 @@ OPN_API int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1, int64_t H2, const fl
                   float* gates1, float* cells1, float* logits_bpt, float* probs, float* frames_boxes, float* hs2,
                   float* gates2, float* cells2, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- OPNet fused backward ------------------------------------------------------------
+ * The reverse recurrences of LSTM2 and LSTM1 and the who-to-track backward between them as ONE persistent kernel (the
+ * mirror image of opn_opnet_fwd): the function of opn_lstm_bwd(H2) -> opn_sgemm(d frames_boxes) -> opn_wtt_bwd ->
+ * opn_lstm_bwd(H1) when no gradient arrives on the who-to-track logits (as in baselines/training_main.py:186-216).
+ * Shipped OPNet config only (H1 = 256, H2 = 512; OPN_ERR_UNSUPPORTED otherwise).
+ *   stash of opn_opnet_fwd (probs, gates1, cells1, gates2, cells2), d_hs2 [B,T,H2] = dLoss / d h2  ->
+ *   d_gates1 [B,T,4*H1], d_gates2 [B,T,4*H2], d_logits [B,T,15] (row layout): the inputs of the time-parallel
+ *   weight-gradient contractions (opn_sgemm).
+ * workspace: opn_opnet_bwd_workspace_bytes(B,T) bytes of scratch (status word as for opn_lstm_status, three rings). */
+OPN_API int64_t opn_opnet_bwd_workspace_bytes(int64_t B, int64_t T);
+OPN_API int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1, int64_t H2, const float* boxes, const float* probs,
+                  const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2, const float* gates1,
+                  const float* cells1, const float* gates2, const float* cells2, const float* d_hs2, float* d_gates1,
+                  float* d_gates2, float* d_logits, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- element-wise / row-wise helpers (transformer_lstm encoder, MLP variant) -------- */
 /* dy[i] = (y[i] > 0) ? dy[i] : 0   (ReLU backward, in place on dy) */
 OPN_API int opn_relu_bwd(int64_t n, const float* y, float* dy, void* stream);

@@ -32,6 +32,8 @@ SIGNATURES = {
     "opn_lstm_status": (c_int, [_P, POINTER(c_uint32)]),
     "opn_opnet_fwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "opn_opnet_fwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 16 + [c_int64, _P]),
+    "opn_opnet_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "opn_opnet_bwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 15 + [c_int64, _P]),
     "opn_wtt_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "opn_wtt_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "opn_relu_bwd": (c_int, [c_int64, _P, _P, _P]),

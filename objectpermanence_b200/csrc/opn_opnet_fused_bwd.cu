@@ -1,0 +1,655 @@
+// OPNet backward as ONE persistent kernel: the reverse recurrence of LSTM2 (512), the who-to-track backward and the
+// reverse recurrence of LSTM1 (256) advance together, one frame per loop iteration -- the mirror image of
+// opn_opnet_fused.cu (autograd backward of baselines/learned_models.py:36-46, triggered at training_main.py:216).
+//
+// LSTM1 at frame t needs d h1[t] = W_pred^T d logits[t], which needs d frames_boxes[t] = W_ih2^T d gates2[t]: the sum over
+// all 2048 gate rows of LSTM2, i.e. over the 32 CTAs of a batch group.  So LSTM1 runs one frame behind LSTM2, every CTA
+// publishes its 64-row share of d frames_boxes (8 videos x 6 values) through a third small ring, and every CTA of the
+// group sums the 32 shares and runs the head backward (15 objects x 8 videos) redundantly, as the forward does.
+// While the CTAs wait for the partial products of one layer they compute the other layer.
+//
+// CTA (slice s of 32, batch group g of 8 videos), 256 threads:
+//   * LSTM2: units [16s, 16s+16): lstm_bwd_mma_kernel<512, 2> (W_hh2 slice as fp16 hi/lo A fragments in registers).
+//   * d frames_boxes share: [6 x 64 rows] . [64 x 8 videos] as 12 more MMAs on the same scaled B fragments (warps 0-3,
+//     one k-step each; W_ih2 slice as A fragments in shared memory).
+//   * head backward: warps 4-7, thread = (video, object), probs / boxes of the frame prefetched with cp.async.
+//   * LSTM1: units [8s, 8s+8): cells on warps 0-3 (lstm_bwd_mma_kernel<256, 1> ownership), the [256 x 32] . [32 x 8]
+//     product on all 8 warps with W_hh1 slice as A fragments in shared memory (32 KB).
+// Outputs: dgates2 [B,T,2048], dgates1 [B,T,1024], d logits [B,T,15] -- what the separate kernels leave for the
+// time-parallel weight-gradient contractions.
+#include <stdlib.h>
+
+#include "opn_mma_common.cuh"
+
+namespace opn {
+
+struct FusedBwdParams {
+    const float *boxes, *probs;                      // [B,T,15,6], [B,T,15]
+    const float *w_hh1, *w_pred, *w_ih2, *w_hh2;     // [1024,256], [15,256], [2048,6], [2048,512]
+    const float *gates1, *cells1, *gates2, *cells2;  // forward stash
+    const float* dhs2;                               // [B,T,512] dLoss / d h2
+    float *dgates1, *dgates2, *dl;                   // [B,T,1024], [B,T,2048], [B,T,15]
+    uint32_t *ring2, *ring1, *ringf;
+    unsigned int* status;
+    int B, T;
+    int group_offset, n_slices;
+};
+
+namespace {
+
+constexpr int H1 = 256, H2 = 512, NOBJ = 15, NFEAT = 6, BOXROW = NOBJ * NFEAT;
+constexpr int NT = 256, NW = 8, NS = 32;
+constexpr int U1 = 8, U2 = 16, R1 = 32, R2 = 64;
+constexpr int KSB1 = R1 / 16, KSB2 = R2 / 16;       // 2, 4 k-steps (own gate rows)
+constexpr int MPW2 = H2 / 16 / NW;                  // 4 m-tiles of W_hh2 columns per warp
+constexpr int MPW1 = H1 / 16 / NW;                  // 2 m-tiles of W_hh1 columns per warp
+constexpr size_t kSlot2 = (size_t)NS * kGroup * H2; // words per ring slot and batch group
+constexpr size_t kSlot1 = (size_t)NS * kGroup * H1;
+constexpr int kSlotF = NS * 64;                     // 32 producers x (48 used + pad) words
+constexpr int kSlots2 = 2, kSlots1 = 4, kSlotsF = 4;   // see the slot-reuse note in the kernel
+
+// shared memory carve-up (bytes)
+constexpr int OFF_A1 = 0;                                        // uint4 [16 mt][KSB1][2][32]   W_hh1^T slice
+constexpr int OFF_AX = OFF_A1 + 16 * KSB1 * 2 * 32 * 16;         // uint4 [KSB2][2][32]          W_ih2^T slice (6 rows used)
+constexpr int OFF_DA2 = OFF_AX + KSB2 * 2 * 32 * 16;             // uint4 [2][KSB2*32]           scaled d gates2 fragments
+constexpr int OFF_DA1 = OFF_DA2 + 2 * KSB2 * 32 * 16;            // uint4 [KSB1*32]              scaled d gates1 fragments
+constexpr int OFF_INV2 = OFF_DA1 + KSB1 * 32 * 16;               // float [2][8] (W_hh2 product), [2][8] (W_ih2 product)
+constexpr int OFF_INV1 = OFF_INV2 + 4 * 8 * 4;                   // float [8]
+constexpr int OFF_DFBP = OFF_INV1 + 8 * 4;                       // float [4 k-steps][8 rows][8]  shares of d frames_boxes
+constexpr int OFF_DFBT = OFF_DFBP + 4 * 8 * 8 * 4;               // float [32 producers][64]
+constexpr int OFF_DFB = OFF_DFBT + NS * 64 * 4;                  // float [8][8]
+constexpr int OFF_DL = OFF_DFB + 8 * 8 * 4;                      // float [8][16]
+constexpr int OFF_WP = OFF_DL + 8 * 16 * 4;                      // float [15][8]   W_pred columns of the CTA's LSTM1 units
+constexpr int OFF_BOX = OFF_WP + 16 * 8 * 4;                     // float [2][8][96]
+constexpr int OFF_PRB = OFF_BOX + 2 * 8 * 96 * 4;                // float [2][8][16]
+constexpr int OFF_RED = OFF_PRB + 2 * 8 * 16 * 4;                // float [8]
+constexpr int OFF_LAND2 = OFF_RED + 64;                          // uint4 [4][NT]  landing slots of the LSTM2 inbox sweep
+constexpr int OFF_LAND1 = OFF_LAND2 + 4 * NT * 16;               // uint4 [4][NT]  landing slots of the LSTM1 inbox sweep
+constexpr int SMEM_BYTES = OFF_LAND1 + 4 * NT * 16;
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {   // .cg: served by L2, the coherence point
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Register-free polling: a sweep over this thread's NV exchange vectors is issued with cp.async into a private landing
+// area a phase before the data is needed; `take_sweep` reads it back and falls back to the polling loads for the
+// (rare) stale vectors.  Each thread only ever touches its own landing slots: no barrier is involved.
+template <int NV, typename AddrFn, typename ValidFn>
+__device__ __forceinline__ void issue_poll(uint4* land, AddrFn addr, ValidFn valid) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (valid(i)) cp_async16(land + i * NT + threadIdx.x, addr(i));
+}
+template <int NV, typename AddrFn, typename ValidFn>
+__device__ __forceinline__ bool take_sweep(uint4 (&v)[NV], const uint4* land, AddrFn addr, ValidFn valid, uint32_t par,
+                                           unsigned int* status, int t, unsigned& fallbacks) {
+    bool stale = false;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (valid(i)) {
+            v[i] = land[i * NT + threadIdx.x];
+            stale |= !ready4(v[i], par);
+        }
+    }
+    if (!stale) return true;
+    ++fallbacks;
+    return gather_flagged(v, addr, valid, par, status, t);
+}
+
+// parity of ring slots that are reused every 4 steps
+__device__ __forceinline__ uint32_t step_parity4(int s) { return ((uint32_t)(s >> 2) & 1u) ^ 1u; }
+
+__global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint4* a1_s = reinterpret_cast<uint4*>(smem + OFF_A1);
+    uint4* ax_s = reinterpret_cast<uint4*>(smem + OFF_AX);
+    uint4* da2_s = reinterpret_cast<uint4*>(smem + OFF_DA2);
+    uint4* da1_s = reinterpret_cast<uint4*>(smem + OFF_DA1);
+    float* inv2_s = reinterpret_cast<float*>(smem + OFF_INV2);   // [buf][8] then [2 + buf][8]
+    float* inv1_s = reinterpret_cast<float*>(smem + OFF_INV1);
+    float* dfbp_s = reinterpret_cast<float*>(smem + OFF_DFBP);
+    float* dfbt_s = reinterpret_cast<float*>(smem + OFF_DFBT);
+    float* dfb_s = reinterpret_cast<float*>(smem + OFF_DFB);
+    float* dl_s = reinterpret_cast<float*>(smem + OFF_DL);
+    float* wp_s = reinterpret_cast<float*>(smem + OFF_WP);
+    float* box_s = reinterpret_cast<float*>(smem + OFF_BOX);
+    float* prb_s = reinterpret_cast<float*>(smem + OFF_PRB);
+    float* red_s = reinterpret_cast<float*>(smem + OFF_RED);
+    uint4* land2_s = reinterpret_cast<uint4*>(smem + OFF_LAND2);
+    uint4* land1_s = reinterpret_cast<uint4*>(smem + OFF_LAND1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int slice = blockIdx.x % p.n_slices;
+    const int group = p.group_offset + blockIdx.x / p.n_slices;
+    const int b0 = group * kGroup;
+    const int T = p.T;
+    const int nvalid = min(kGroup, p.B - b0);
+    const int u0_1 = slice * U1, u0_2 = slice * U2;
+    uint32_t* ring2 = p.ring2 + (size_t)group * (kSlots2 * kSlot2);
+    uint32_t* ring1 = p.ring1 + (size_t)group * (kSlots1 * kSlot1);
+    uint32_t* ringf = p.ringf + (size_t)group * (kSlotsF * kSlotF);
+
+    for (int i = tid; i < (OFF_WP - OFF_DA2) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_DA2)[i] = 0u;
+    for (int i = tid; i < (OFF_RED - OFF_BOX) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_BOX)[i] = 0u;
+    __syncthreads();
+    if (tid < 40) inv2_s[tid] = 1.0f;   // inv2 (32 floats) + inv1 (8 floats), contiguous
+
+    // ---- W_hh2: A[m = column k][kk = own row lr] in registers (as lstm_bwd_mma_kernel<512, 2>) ------------------
+    auto wrow2 = [&](int lr) { return p.w_hh2 + (size_t)((lr & 3) * H2 + u0_2 + (lr >> 2)) * H2; };
+    auto wrow1 = [&](int lr) { return p.w_hh1 + (size_t)((lr & 3) * H1 + u0_1 + (lr >> 2)) * H1; };
+    float wmax = 0.0f;
+    for (int mi = 0; mi < MPW2; ++mi)
+        for (int ks = 0; ks < KSB2; ++ks) {
+            const int kc = (warp * MPW2 + mi) * 16 + g, lr = 16 * ks + 2 * tq;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int l = lr + (q & 1) + 8 * (q >> 1);
+                wmax = fmaxf(wmax, fmaxf(fabsf(__ldg(wrow2(l) + kc)), fabsf(__ldg(wrow2(l) + kc + 8))));
+            }
+        }
+    float wscale2, winv2;
+    weight_scale<NW>(wmax, red_s, wscale2, winv2);
+    uint32_t ahi[MPW2][KSB2][4], alo[MPW2][KSB2][4];
+#pragma unroll
+    for (int mi = 0; mi < MPW2; ++mi)
+#pragma unroll
+        for (int ks = 0; ks < KSB2; ++ks) {
+            const int kc = (warp * MPW2 + mi) * 16 + g, lr = 16 * ks + 2 * tq;
+            split2(__ldg(wrow2(lr) + kc) * wscale2, __ldg(wrow2(lr + 1) + kc) * wscale2, ahi[mi][ks][0], alo[mi][ks][0]);
+            split2(__ldg(wrow2(lr) + kc + 8) * wscale2, __ldg(wrow2(lr + 1) + kc + 8) * wscale2, ahi[mi][ks][1], alo[mi][ks][1]);
+            split2(__ldg(wrow2(lr + 8) + kc) * wscale2, __ldg(wrow2(lr + 9) + kc) * wscale2, ahi[mi][ks][2], alo[mi][ks][2]);
+            split2(__ldg(wrow2(lr + 8) + kc + 8) * wscale2, __ldg(wrow2(lr + 9) + kc + 8) * wscale2, ahi[mi][ks][3], alo[mi][ks][3]);
+        }
+    // ---- W_hh1: the same orientation, 16 m-tiles x 2 k-steps of fragments in shared memory -----------------------
+    float winv1, winvx;
+    {
+        auto frag1 = [&](int e, float scale, uint4& hi, uint4& lo, float& m) {   // e = (mt*KSB1 + ks)*32 + lane'
+            const int l = e & 31, ks = (e >> 5) % KSB1, mt = e / (32 * KSB1);
+            const int kc = mt * 16 + (l >> 2), lr = 16 * ks + 2 * (l & 3);
+            const float v[8] = {__ldg(wrow1(lr) + kc),     __ldg(wrow1(lr + 1) + kc),     __ldg(wrow1(lr) + kc + 8),
+                                __ldg(wrow1(lr + 1) + kc + 8), __ldg(wrow1(lr + 8) + kc), __ldg(wrow1(lr + 9) + kc),
+                                __ldg(wrow1(lr + 8) + kc + 8), __ldg(wrow1(lr + 9) + kc + 8)};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m = fmaxf(m, fabsf(v[q]));
+            split2(v[0] * scale, v[1] * scale, hi.x, lo.x);
+            split2(v[2] * scale, v[3] * scale, hi.y, lo.y);
+            split2(v[4] * scale, v[5] * scale, hi.z, lo.z);
+            split2(v[6] * scale, v[7] * scale, hi.w, lo.w);
+        };
+        float m = 0.0f;
+        uint4 hi, lo;
+        for (int e = tid; e < 16 * KSB1 * 32; e += NT) frag1(e, 1.0f, hi, lo, m);
+        float wscale1;
+        weight_scale<NW>(m, red_s, wscale1, winv1);
+        for (int e = tid; e < 16 * KSB1 * 32; e += NT) {
+            frag1(e, wscale1, hi, lo, m);
+            a1_s[(e >> 5) * 64 + (e & 31)] = hi;
+            a1_s[(e >> 5) * 64 + 32 + (e & 31)] = lo;
+        }
+        // ---- W_ih2^T slice: A[m = feature f (6 of 16)][kk = own row lr] -------------------------------------------
+        auto fragx = [&](int e, float scale, uint4& h4, uint4& l4, float& mx) {   // e = ks*32 + lane'
+            const int l = e & 31, ks = e >> 5, f = l >> 2, lr = 16 * ks + 2 * (l & 3);
+            auto w = [&](int row) {
+                return f < NFEAT ? __ldg(p.w_ih2 + (size_t)((row & 3) * H2 + u0_2 + (row >> 2)) * NFEAT + f) : 0.0f;
+            };
+            const float v0 = w(lr), v1 = w(lr + 1), v2 = w(lr + 8), v3 = w(lr + 9);
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3))));
+            split2(v0 * scale, v1 * scale, h4.x, l4.x);   // a0: (m g, kk 2t..)
+            h4.y = 0u, l4.y = 0u;                         // a1: (m g+8, ..) rows 8..15 are padding
+            split2(v2 * scale, v3 * scale, h4.z, l4.z);   // a2: (m g, kk 2t+8..)
+            h4.w = 0u, l4.w = 0u;
+        };
+        m = 0.0f;
+        for (int e = tid; e < KSB2 * 32; e += NT) fragx(e, 1.0f, hi, lo, m);
+        float wscalex;
+        weight_scale<NW>(m, red_s, wscalex, winvx);
+        for (int e = tid; e < KSB2 * 32; e += NT) {
+            fragx(e, wscalex, hi, lo, m);
+            ax_s[(e >> 5) * 64 + (e & 31)] = hi;
+            ax_s[(e >> 5) * 64 + 32 + (e & 31)] = lo;
+        }
+        for (int e = tid; e < NOBJ * U1; e += NT) wp_s[e] = __ldg(p.w_pred + (size_t)(e / U1) * H1 + u0_1 + e % U1);
+    }
+
+    // ---- cell ownership ------------------------------------------------------------------------------------------
+    // LSTM2: warp w = video w; lane l -> unit 4*(l&3) + ((l>>3)&3), half (l>>2)&1
+    const int bl2 = warp, ul2 = 4 * (lane & 3) + ((lane >> 3) & 3), half2 = (lane >> 2) & 1;
+    const int uu2 = u0_2 + ul2;
+    const bool valid2 = b0 + bl2 < p.B;
+    const size_t row2 = (size_t)(valid2 ? b0 + bl2 : 0) * T;
+    const int lrp2 = ul2 * 4 + 2 * half2;
+    const int da_word2 = 4 * ((lrp2 >> 4) * 32 + bl2 * 4 + (((lrp2 & 15) & 7) >> 1)) + ((lrp2 & 15) >> 3);
+    // LSTM1 (warps 0-3): warp w = videos 2w, 2w+1; lane l -> video 2w + (l>>4), unit 4*(l&1) + ((l>>2)&3), half (l>>1)&1
+    const int bl1 = 2 * (warp & 3) + (lane >> 4), ul1 = 4 * (lane & 1) + ((lane >> 2) & 3), half1 = (lane >> 1) & 1;
+    const unsigned vmask1 = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    const int uu1 = u0_1 + ul1;
+    const bool valid1 = warp < 4 && b0 + bl1 < p.B;
+    const size_t row1 = (size_t)(valid1 ? b0 + bl1 : 0) * T;
+    const int lrp1 = ul1 * 4 + 2 * half1;
+    const int da_word1 = 4 * ((lrp1 >> 4) * 32 + bl1 * 4 + (((lrp1 & 15) & 7) >> 1)) + ((lrp1 & 15) >> 3);
+    // head (warps 4-7): video hb, object ho
+    const int hb = (tid - 128) >> 4, ho = tid & 15;
+
+    // word offsets of this thread's first published partial sums (see the publish loops)
+    const int pub2_off = ((warp * MPW2) * kGroup * NS + slice) * U2 + g + (2 * tq) * (NS * U2);
+    const int pub1_off = ((warp * MPW1 * 2) * kGroup * NS + slice) * U1 + g + (2 * tq) * (NS * U1);
+
+    float dc2 = 0.0f, dhr2 = 0.0f, dc1 = 0.0f, dhr1 = 0.0f;
+    float si = 0.f, sf = 0.f, sg = 0.f, so = 0.f, sc = 0.f, scp = 0.f, sdh = 0.f;   // LSTM2 stash of the current frame
+    float qi = 0.f, qf = 0.f, qg = 0.f, qo = 0.f, qc = 0.f, qcp = 0.f;              // LSTM1 stash of the current frame
+    auto load_stash2 = [&](int t) {
+        const size_t row = row2 + t;
+        const float* gp = p.gates2 + row * (size_t)(4 * H2) + uu2;
+        si = __ldg(gp), sf = __ldg(gp + H2), sg = __ldg(gp + 2 * H2), so = __ldg(gp + 3 * H2);
+        sc = __ldg(p.cells2 + row * H2 + uu2);
+        scp = (t > 0) ? __ldg(p.cells2 + (row - 1) * H2 + uu2) : 0.0f;
+        sdh = __ldg(p.dhs2 + row * H2 + uu2);
+    };
+    auto load_stash1 = [&](int t) {
+        const size_t row = row1 + t;
+        const float* gp = p.gates1 + row * (size_t)(4 * H1) + uu1;
+        qi = __ldg(gp), qf = __ldg(gp + H1), qg = __ldg(gp + 2 * H1), qo = __ldg(gp + 3 * H1);
+        qc = __ldg(p.cells1 + row * H1 + uu1);
+        qcp = (t > 0) ? __ldg(p.cells1 + (row - 1) * H1 + uu1) : 0.0f;
+    };
+    // probs / boxes of frame t -> shared memory buffer t&1 (asynchronous copies, no registers)
+    auto prefetch_head = [&](int t) {   // warp w copies video w: 90 box values + 15 probabilities
+        if (t < 0 || warp >= nvalid) return;
+        const float* src = p.boxes + ((size_t)(b0 + warp) * T + t) * BOXROW + lane;
+        float* dst = box_s + (t & 1) * (8 * 96) + warp * 96 + lane;
+        cp_async4(dst, src);
+        cp_async4(dst + 32, src + 32);
+        if (lane < BOXROW - 64) cp_async4(dst + 64, src + 64);
+        if (lane < NOBJ) cp_async4(prb_s + (t & 1) * (8 * 16) + warp * 16 + lane, p.probs + ((size_t)(b0 + warp) * T + t) * NOBJ + lane);
+    };
+    if (valid2) load_stash2(T - 1);
+    if (valid1) load_stash1(T - 1);
+    prefetch_head(T - 1);
+    int my_abort = 0;
+    unsigned nfall2 = 0, nfall1 = 0, nfallf = 0;   // statistics (thread 0 of CTA 0 -> status[8..10]): sweeps that came back stale
+    __syncthreads();
+
+    // iteration s: LSTM2 frame t2 = T-1-s (s < T); head backward + LSTM1 frame t1 = T-s (s >= 1)
+    PH_DECL
+    for (int s = 0; s <= T; ++s) {
+        const int t2 = T - 1 - s, t1 = T - s;
+        const int buf = s & 1;
+        float v0 = 0.0f, v1 = 0.0f;
+        PH(7);  // LSTM1 MMAs + publish of the previous iteration
+        // ================= LSTM2 frame t2 ===========================================================================
+        if (s < T) {
+            if (s >= 1) {
+                // recurrent part of dh2[t2]: sum the producers' partial products of step s-1 for the own units
+                const int sp = s - 1;
+                const uint32_t* src = ring2 + (size_t)(sp & 1) * kSlot2 + (size_t)slice * kGroup * NS * U2;
+                const uint32_t par = step_parity(sp);
+                uint4 v[4];
+                auto vec_valid = [&](int i) { return warp < nvalid; };
+                cp_async_wait<1>();   // the inbox sweep of the previous iteration; its head prefetch (the last group) may still fly
+                if (!take_sweep(v, land2_s, [&](int i) { return src + ((size_t)warp * NS * 4 + i * 32 + lane) * 4; }, vec_valid, par,
+                                p.status, s, nfall2))
+                    my_abort = 1;
+                float r4[4];
+                const bool ok = warp < nvalid;
+                r4[0] = ok ? (__uint_as_float(v[0].x) + __uint_as_float(v[1].x)) + (__uint_as_float(v[2].x) + __uint_as_float(v[3].x)) : 0.f;
+                r4[1] = ok ? (__uint_as_float(v[0].y) + __uint_as_float(v[1].y)) + (__uint_as_float(v[2].y) + __uint_as_float(v[3].y)) : 0.f;
+                r4[2] = ok ? (__uint_as_float(v[0].z) + __uint_as_float(v[1].z)) + (__uint_as_float(v[2].z) + __uint_as_float(v[3].z)) : 0.f;
+                r4[3] = ok ? (__uint_as_float(v[0].w) + __uint_as_float(v[1].w)) + (__uint_as_float(v[2].w) + __uint_as_float(v[3].w)) : 0.f;
+                butterfly_stage<4, 1, 4>(r4, (lane & 16) != 0, 16);
+                butterfly_stage<2, 0, 4>(r4, (lane & 8) != 0, 8);
+                dhr2 = r4[0] + __shfl_xor_sync(0xffffffffu, r4[0], 4);
+            }
+            PH(0);  // gather + reduce of the LSTM2 partial products
+        }
+        if (s >= 1) {
+            // d frames_boxes shares of frame t1 (published an iteration ago): straight into the summation tile
+            const uint32_t* srcf = ringf + (size_t)((s - 1) & 3) * kSlotF;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (((tid + NT * i) & 15) < 12) cp_async16(reinterpret_cast<uint4*>(dfbt_s) + tid + NT * i, srcf + (size_t)(tid + NT * i) * 4);
+        }
+        cp_async_commit();   // group "dfb"
+        if (s < T) {
+            if (valid2) {
+                const float dh = sdh + dhr2;
+                const float tc = tanh_sfu(sc);
+                const float d_o = dh * tc;
+                const float dc = fmaf(dh * so, 1.0f - tc * tc, dc2);
+                dc2 = dc * sf;
+                if (half2 == 0) {
+                    v0 = dc * sg * si * (1.0f - si);
+                    v1 = dc * scp * sf * (1.0f - sf);
+                } else {
+                    v0 = dc * si * (1.0f - sg * sg);
+                    v1 = d_o * so * (1.0f - so);
+                }
+                // per-video power-of-two scale (the products with W_hh2 need it for t2 > 0, the one with W_ih2 always)
+                const unsigned mbits = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(fabsf(v0), fabsf(v1))) & 0x7fffffffu);
+                float sc2, inv2;
+                pow2_scale(__uint_as_float(mbits), 11, sc2, inv2);
+                uint32_t hi, lo;
+                split2(v0 * sc2, v1 * sc2, hi, lo);
+                uint32_t* w = reinterpret_cast<uint32_t*>(da2_s + buf * (KSB2 * 32)) + da_word2;
+                w[0] = hi;
+                w[2] = lo;
+                if (ul2 == 0 && half2 == 0) {
+                    inv2_s[buf * 8 + bl2] = inv2 * winv2;
+                    inv2_s[(2 + buf) * 8 + bl2] = inv2 * winvx;
+                }
+            }
+        }
+        PH(1);  // LSTM2 cell backward
+        if (__syncthreads_or(my_abort)) break;   // (A) d gates2 fragments of this frame complete
+        PH(2);  // barrier A
+        if (s < T) {
+            if (valid2) {
+                float* dg = p.dgates2 + (row2 + t2) * (size_t)(4 * H2) + uu2 + (half2 ? 2 * H2 : 0);
+                dg[0] = v0;
+                dg[H2] = v1;
+                if (t2 > 0) load_stash2(t2 - 1);
+            }
+            const uint4* bfp = da2_s + buf * (KSB2 * 32);
+            uint4 bf[KSB2];
+#pragma unroll
+            for (int ks = 0; ks < KSB2; ++ks) bf[ks] = bfp[ks * 32 + lane];
+            if (t2 > 0) {
+                const uint32_t par = step_parity(s);
+                uint32_t* pub2 = ring2 + (size_t)buf * kSlot2 + pub2_off;
+                const float inv0 = inv2_s[buf * 8 + 2 * tq], inv1 = inv2_s[buf * 8 + 2 * tq + 1];
+#pragma unroll
+                for (int mi = 0; mi < MPW2; ++mi) {
+                    float dm[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f}, dt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < KSB2; ++ks) {   // three independent accumulation chains of KSB2 MMAs
+                        opn::mma_f16(dm, ahi[mi][ks], bf[ks].x, bf[ks].y);
+                        opn::mma_f16(ds, ahi[mi][ks], bf[ks].z, bf[ks].w);
+                        opn::mma_f16(dt, alo[mi][ks], bf[ks].x, bf[ks].y);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ds[q] += dt[q];
+                    // column k = (warp*MPW2 + mi)*16 + g + 8*(q>>1) belongs to consumer warp*MPW2 + mi, unit g + 8*(q>>1);
+                    // word [consumer][video b][producer = slice][unit].  Videos past the end of the batch are stored too
+                    // (zeros; nobody reads them): no branch per word, compile-time offsets from one base pointer.
+                    uint32_t* base = pub2 + mi * (kGroup * NS * U2);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        st_flagged(base + (q >> 1) * 8 + (q & 1) * (NS * U2), (dm[q] + ds[q]) * ((q & 1) ? inv1 : inv0), par);
+                }
+            }
+            if (warp < 4) {
+                // share of d frames_boxes[t2]: [6 features] x [this warp's 16 own rows] . [16 x 8 videos]
+                float dm[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint4 ah = ax_s[warp * 64 + lane], al = ax_s[warp * 64 + 32 + lane];
+                const uint4 bw = bfp[warp * 32 + lane];
+                mma_f16(dm, ah, bw.x, bw.y);
+                mma_f16(ds, ah, bw.z, bw.w);
+                mma_f16(ds, al, bw.x, bw.y);
+                // D: (feature g, videos 2tq, 2tq+1); rows g >= 8 are padding
+                *reinterpret_cast<float2*>(dfbp_s + (warp * 8 + g) * 8 + 2 * tq) = make_float2(dm[0] + ds[0], dm[1] + ds[1]);
+            }
+        }
+        PH(3);  // LSTM2 MMAs + publish + d frames_boxes share
+        __syncthreads();   // (B0) the four k-step shares of d frames_boxes[t2] are in shared memory
+        if (s < T && tid < 48) {
+            const int f = tid >> 3, b = tid & 7;
+            const float sum = (dfbp_s[(0 * 8 + f) * 8 + b] + dfbp_s[(1 * 8 + f) * 8 + b]) +
+                              (dfbp_s[(2 * 8 + f) * 8 + b] + dfbp_s[(3 * 8 + f) * 8 + b]);
+            st_flagged(ringf + (size_t)(s & 3) * kSlotF + slice * 64 + tid, sum * inv2_s[(2 + buf) * 8 + b], step_parity4(s));
+        }
+        if (warp < 4 && s >= 2) {
+            // partial products of LSTM1 step s-2 (published at the end of the previous iteration, a whole LSTM2 phase ago)
+            const uint32_t* src1 = ring1 + (size_t)((s - 2) & 3) * kSlot1 + (size_t)slice * kGroup * NS * U1;
+            issue_poll<4>(land1_s, [&](int i) { return src1 + ((size_t)(2 * warp + (i >> 1)) * NS * 2 + (i & 1) * 32 + lane) * 4; },
+                          [&](int i) { return 2 * warp + (i >> 1) < nvalid; });
+        }
+        cp_async_commit();   // group "inbox1"
+        if (s == 0) {
+            prefetch_head(T - 2);
+            cp_async_commit();   // group "tail"
+            continue;
+        }
+
+        // ================= head backward + LSTM1, frame t1 = T-s =====================================================
+        {
+            // d frames_boxes[t1]: the 32 shares published in the previous iteration (ring slot (s-1)&3) were copied into
+            // the summation tile at the top of this iteration; verify their ready bits, re-fetch what was stale
+            const uint32_t* src = ringf + (size_t)((s - 1) & 3) * kSlotF;
+            const uint32_t par = step_parity4(s - 1);
+            cp_async_wait<1>();   // everything but the LSTM1 inbox sweep just issued
+            // vector idx = tid + 256*i of the [32][64]-word tile: producer idx/16, words 4*(idx%16)..; 48 of 64 used
+            auto vec_valid = [&](int i) { return ((tid + NT * i) & 15) < 12; };
+            bool stale = false;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (vec_valid(i)) stale |= !ready4(reinterpret_cast<const uint4*>(dfbt_s)[tid + NT * i], par);
+            if (stale) {
+                ++nfallf;
+                uint4 v[2];
+                if (!gather_flagged(v, [&](int i) { return src + (size_t)(tid + NT * i) * 4; }, vec_valid, par, p.status, s))
+                    my_abort = 1;
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (vec_valid(i)) reinterpret_cast<uint4*>(dfbt_s)[tid + NT * i] = v[i];
+            }
+        }
+        PH(4);  // barrier B0 + publish + gather of the d frames_boxes shares
+        if (__syncthreads_or(my_abort)) break;    // (B1)
+        if (tid < 192) {   // 4 threads per value, 8 producers each, two shuffles
+            const int out = tid >> 2, part = tid & 3;
+            float sum = 0.0f;
+#pragma unroll
+            for (int pr = 0; pr < 8; ++pr) sum += dfbt_s[(part * 8 + pr) * 64 + out];
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (part == 0) dfb_s[(out & 7) * 8 + (out >> 3)] = sum;   // [video][feature]
+        }
+        __syncthreads();                          // (B2)
+        if (s < T - 1) {
+            // partial products of LSTM2 step s (published behind barrier A of this iteration, ~2500 clocks ago), needed at
+            // the top of the next iteration: the sweep lands while the head, the LSTM1 cells and MMAs run
+            const uint32_t* src2 = ring2 + (size_t)(s & 1) * kSlot2 + (size_t)slice * kGroup * NS * U2;
+            issue_poll<4>(land2_s, [&](int i) { return src2 + ((size_t)warp * NS * 4 + i * 32 + lane) * 4; },
+                          [&](int i) { return warp < nvalid; });
+        }
+        cp_async_commit();   // group "inbox2"
+        PH(5);  // sum of the shares (barriers B1, B2)
+        if (warp >= 4) {
+            // ---- head backward: thread = (video hb, object ho) ------------------------------------------------------
+            const float* bx = box_s + (t1 & 1) * (8 * 96) + hb * 96 + ho * NFEAT;
+            const float po = (ho < NOBJ) ? prb_s[(t1 & 1) * (8 * 16) + hb * 16 + ho] : 0.0f;
+            float dp = 0.0f;
+            if (ho < NOBJ) {
+#pragma unroll
+                for (int c = 0; c < NFEAT; ++c) dp = fmaf(dfb_s[hb * 8 + c], bx[c], dp);
+            }
+            float dot = po * dp;
+#pragma unroll
+            for (int m = 8; m > 0; m >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, m);
+            const float dlv = po * (dp - dot);
+            dl_s[hb * 16 + ho] = (ho < NOBJ) ? dlv : 0.0f;
+            if (slice == 0 && ho < NOBJ && b0 + hb < p.B) p.dl[((size_t)(b0 + hb) * T + t1) * NOBJ + ho] = dlv;
+        } else if (s >= 2) {
+            // ---- recurrent part of dh1[t1]: partial products of LSTM1 step s-2 (published in the previous iteration) ---
+            const int sp = s - 2;
+            const uint32_t* src = ring1 + (size_t)(sp & 3) * kSlot1 + (size_t)slice * kGroup * NS * U1;
+            const uint32_t par = step_parity4(sp);
+            uint4 v[4];
+            auto vec_b = [&](int i) { return 2 * warp + (i >> 1); };
+            auto vec_valid = [&](int i) { return vec_b(i) < nvalid; };
+            cp_async_wait<1>();   // everything but the LSTM2 inbox sweep just issued
+            if (!take_sweep(v, land1_s, [&](int i) { return src + ((size_t)vec_b(i) * NS * 2 + (i & 1) * 32 + lane) * 4; }, vec_valid, par,
+                            p.status, s, nfall1))
+                my_abort = 1;
+            float f[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = vec_valid(i);
+                f[i][0] = ok ? __uint_as_float(v[i].x) : 0.0f;
+                f[i][1] = ok ? __uint_as_float(v[i].y) : 0.0f;
+                f[i][2] = ok ? __uint_as_float(v[i].z) : 0.0f;
+                f[i][3] = ok ? __uint_as_float(v[i].w) : 0.0f;
+            }
+            float r8[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r8[j] = f[0][j] + f[1][j];
+                r8[4 + j] = f[2][j] + f[3][j];
+            }
+            butterfly_stage<8, 2, 8>(r8, (lane & 16) != 0, 16);
+            butterfly_stage<4, 1, 8>(r8, (lane & 8) != 0, 8);
+            butterfly_stage<2, 0, 8>(r8, (lane & 4) != 0, 4);
+            dhr1 = r8[0] + __shfl_xor_sync(0xffffffffu, r8[0], 2);
+        }
+        if (__syncthreads_or(my_abort)) break;    // (B3) d logits of frame t1 in shared memory
+        float w0 = 0.0f, w1 = 0.0f;
+        if (valid1) {
+            float dh = dhr1, dhb = 0.0f, dhc = 0.0f;
+#pragma unroll
+            for (int o = 0; o < NOBJ; o += 3) {
+                dh = fmaf(dl_s[bl1 * 16 + o], wp_s[o * U1 + ul1], dh);
+                dhb = fmaf(dl_s[bl1 * 16 + o + 1], wp_s[(o + 1) * U1 + ul1], dhb);
+                dhc = fmaf(dl_s[bl1 * 16 + o + 2], wp_s[(o + 2) * U1 + ul1], dhc);
+            }
+            dh += dhb + dhc;
+            const float tc = tanh_sfu(qc);
+            const float d_o = dh * tc;
+            const float dc = fmaf(dh * qo, 1.0f - tc * tc, dc1);
+            dc1 = dc * qf;
+            if (half1 == 0) {
+                w0 = dc * qg * qi * (1.0f - qi);
+                w1 = dc * qcp * qf * (1.0f - qf);
+            } else {
+                w0 = dc * qi * (1.0f - qg * qg);
+                w1 = d_o * qo * (1.0f - qo);
+            }
+            if (t1 > 0) {
+                const unsigned mbits = __reduce_max_sync(vmask1, __float_as_uint(fmaxf(fabsf(w0), fabsf(w1))) & 0x7fffffffu);
+                float sc1, i1;
+                pow2_scale(__uint_as_float(mbits), 11, sc1, i1);
+                uint32_t hi, lo;
+                split2(w0 * sc1, w1 * sc1, hi, lo);
+                uint32_t* w = reinterpret_cast<uint32_t*>(da1_s) + da_word1;
+                w[0] = hi;
+                w[2] = lo;
+                if (ul1 == 0 && half1 == 0) inv1_s[bl1] = i1 * winv1;
+            }
+        }
+        PH(6);  // head backward | gather of the LSTM1 partial products, barrier B3, LSTM1 cell backward
+        __syncthreads();                          // (B4) d gates1 fragments complete
+        if (valid1) {
+            float* dg = p.dgates1 + (row1 + t1) * (size_t)(4 * H1) + uu1 + (half1 ? 2 * H1 : 0);
+            dg[0] = w0;
+            dg[H1] = w1;
+            if (t1 > 0) load_stash1(t1 - 1);
+        }
+        prefetch_head(t1 - 2);                    // buffer (t1-2)&1 == t1&1: consumed before barrier B3
+        cp_async_commit();   // group "tail"
+        if (t1 > 0) {
+            // partial1[k][b] = sum_{own rows} W_hh1[row][k] * da1[b][row]: 2 m-tiles of 16 columns per warp
+            const int s1 = s - 1;
+            const uint32_t par = step_parity4(s1);
+            uint32_t* pub1 = ring1 + (size_t)(s1 & 3) * kSlot1 + pub1_off;
+            uint4 bf[KSB1];
+#pragma unroll
+            for (int ks = 0; ks < KSB1; ++ks) bf[ks] = da1_s[ks * 32 + lane];
+            const float inv0 = inv1_s[2 * tq], inv1 = inv1_s[2 * tq + 1];
+#pragma unroll
+            for (int mi = 0; mi < MPW1; ++mi) {
+                const int mt = warp * MPW1 + mi;
+                float dm[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < KSB1; ++ks) {
+                    const uint4 ah = a1_s[(mt * KSB1 + ks) * 64 + lane], al = a1_s[(mt * KSB1 + ks) * 64 + 32 + lane];
+                    mma_f16(dm, ah, bf[ks].x, bf[ks].y);
+                    mma_f16(ds, ah, bf[ks].z, bf[ks].w);
+                    mma_f16(ds, al, bf[ks].x, bf[ks].y);
+                }
+                // column k = mt*16 + g + 8*(q>>1): consumers 2*mt + (q>>1) (8 units each), unit g
+                uint32_t* base = pub1 + mi * (2 * kGroup * NS * U1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    st_flagged(base + (q >> 1) * (kGroup * NS * U1) + (q & 1) * (NS * U1), (dm[q] + ds[q]) * ((q & 1) ? inv1 : inv0),
+                               par);
+            }
+        }
+    }
+    PH_STORE(p.status);
+    if (blockIdx.x == 0 && tid == 0) {
+        p.status[8] = nfall2;
+        p.status[9] = nfall1;
+        p.status[10] = nfallf;
+    }
+}
+
+struct FusedBwdLayout {
+    size_t status_off, ring2_off, ring1_off, ringf_off, total;
+};
+FusedBwdLayout fused_bwd_layout(int64_t B) {
+    const size_t groups = (size_t)((B + kGroup - 1) / kGroup);
+    FusedBwdLayout l;
+    l.status_off = 0;
+    l.ring2_off = 4096;
+    l.ring1_off = l.ring2_off + groups * kSlots2 * kSlot2 * sizeof(float);
+    l.ringf_off = l.ring1_off + groups * kSlots1 * kSlot1 * sizeof(float);
+    l.total = l.ringf_off + groups * kSlotsF * kSlotF * sizeof(float);
+    return l;
+}
+
+}  // namespace
+}  // namespace opn
+
+using namespace opn;
+
+extern "C" int64_t opn_opnet_bwd_workspace_bytes(int64_t B, int64_t T) {
+    (void)T;
+    if (B <= 0) return 0;
+    return (int64_t)fused_bwd_layout(B).total;
+}
+
+extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* probs,
+                             const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2,
+                             const float* gates1, const float* cells1, const float* gates2, const float* cells2,
+                             const float* dhs2, float* dgates1, float* dgates2, float* d_logits, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    OPN_CHECK_ARG(B > 0 && T > 0, "opnet_bwd: B and T must be positive");
+    if (H1_ != H1 || H2_ != H2) {
+        set_error("opnet_bwd: the fused backward exists for the shipped OPNet config (H1 = 256, H2 = 512), got %lld / %lld",
+                  (long long)H1_, (long long)H2_);
+        return OPN_ERR_UNSUPPORTED;
+    }
+    OPN_CHECK_ARG(boxes && probs && w_hh1 && w_pred && w_ih2 && w_hh2 && gates1 && cells1 && gates2 && cells2 && dhs2 && dgates1 &&
+                      dgates2 && d_logits && workspace,
+                  "opnet_bwd: null pointer");
+    const FusedBwdLayout l = fused_bwd_layout(B);
+    OPN_CHECK_ARG(workspace_bytes >= (int64_t)l.total, "opnet_bwd: workspace too small (%lld < %lld)",
+                  (long long)workspace_bytes, (long long)l.total);
+    cudaStream_t s = as_stream(stream);
+    char* ws = static_cast<char*>(workspace);
+    OPN_CUDA(cudaMemsetAsync(ws, 0, l.total, s));
+    FusedBwdParams p;
+    p.boxes = boxes, p.probs = probs;
+    p.w_hh1 = w_hh1, p.w_pred = w_pred, p.w_ih2 = w_ih2, p.w_hh2 = w_hh2;
+    p.gates1 = gates1, p.cells1 = cells1, p.gates2 = gates2, p.cells2 = cells2;
+    p.dhs2 = dhs2;
+    p.dgates1 = dgates1, p.dgates2 = dgates2, p.dl = d_logits;
+    p.ring2 = reinterpret_cast<uint32_t*>(ws + l.ring2_off);
+    p.ring1 = reinterpret_cast<uint32_t*>(ws + l.ring1_off);
+    p.ringf = reinterpret_cast<uint32_t*>(ws + l.ringf_off);
+    p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
+    p.B = (int)B, p.T = (int)T;
+    p.group_offset = 0, p.n_slices = NS;
+    return launch_ring(opnet_bwd_fused_kernel, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+}

@@ -338,6 +338,7 @@ class OPNetTrunkFn(torch.autograd.Function):
         sgemm(boxes, w_ih1, xproj1, trans_a=False, trans_b=True, M=B * T, N=4 * H1, K=NO * F, lda=NO * F, ldb=NO * F,
               ldc=4 * H1)
         need_grad = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)   # backward sees None (not zeros) when an output carries no gradient
         hs1 = torch.empty(B, T, H1, **f32)
         hs2 = torch.empty(B, T, H2, **f32)
         logits = torch.empty(B, 15, T, **f32)
@@ -370,6 +371,25 @@ class OPNetTrunkFn(torch.autograd.Function):
         if dhs2 is None:
             dhs2 = torch.zeros_like(hs2)
         H2 = w_hh2.shape[1]
+        if dlogits is None and os.environ.get("OPN_OPNET_FUSED_BWD", "1") not in ("0", ""):
+            # both reverse recurrences and the who-to-track backward in one persistent kernel (opn_opnet_fused_bwd.cu)
+            lib = _lib.load()
+            H1 = w_hh1.shape[1]
+            dev = boxes.device
+            dgates2 = torch.empty(B, T, 4 * H2, device=dev, dtype=torch.float32)
+            dgates1 = torch.empty(B, T, 4 * H1, device=dev, dtype=torch.float32)
+            dl = torch.empty(B, T, 15, device=dev, dtype=torch.float32)
+            ws = torch.empty(lib.opn_opnet_bwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+            rc = lib.opn_opnet_bwd(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
+                                   w_ih2.data_ptr(), w_hh2.data_ptr(), gates1.data_ptr(), cells1.data_ptr(),
+                                   gates2.data_ptr(), cells2.data_ptr(), dhs2.contiguous().data_ptr(), dgates1.data_ptr(),
+                                   dgates2.data_ptr(), dl.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            _lib.check(rc, "opn_opnet_bwd")
+            _lstm_check(ws, "opn_opnet_bwd")
+            dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, need[4], need[5])
+            dw_pred = _wtt_weight_grad(hs1, dl) if need[3] else None
+            dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, boxes.reshape(B, T, -1), hs1, w_ih1, w_hh1, need[1], need[2])
+            return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
         dgates2 = _lstm_recurrence_backward(w_hh2, gates2, cells2, dhs2)
         dfb = torch.empty_like(fb)
         sgemm(dgates2, w_ih2, dfb, trans_a=False, trans_b=False, M=B * T, N=6, K=4 * H2, lda=4 * H2, ldb=6, ldc=6)

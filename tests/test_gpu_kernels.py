@@ -235,10 +235,13 @@ def test_lstm_unsupported_hidden_size(cuda_device):
 
 
 # ---- fused OPNet forward ----------------------------------------------------------------------
-@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (11, 37), (32, 64), (70, 9)])
-def test_opnet_fused_forward_matches_separate_kernels(cuda_device, monkeypatch, B, T):
-    """LSTM1 + who-to-track + LSTM2 as one persistent kernel against the chain of separate kernels and the fp64
-    oracle: outputs, every stash tensor the backward pass reads, and the gradients through both paths."""
+@pytest.mark.parametrize("bwd", ["fused", "separate"])
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (11, 37), (32, 64), (70, 9), (8, 300)])
+def test_opnet_fused_forward_matches_separate_kernels(cuda_device, monkeypatch, B, T, bwd):
+    """LSTM1 + who-to-track + LSTM2 as one persistent kernel (and the mirror-image fused backward: both reverse
+    recurrences + the who-to-track backward) against the chain of separate kernels and the fp64 oracle: outputs and the
+    gradients of all five weight matrices through every path."""
+    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "1" if bwd == "fused" else "0")
     H1, H2 = 256, 512
     boxes = torch.rand(B, T, 15, 6, generator=torch.Generator().manual_seed(5 + B)) * (torch.rand(B, T, 15, 1) > 0.3)
     w = {"ih1": _rand((4 * H1, 90), 1, 1 / math.sqrt(H1)), "hh1": _rand((4 * H1, H1), 2, 1 / math.sqrt(H1)),
@@ -275,9 +278,34 @@ def test_opnet_fused_forward_matches_separate_kernels(cuda_device, monkeypatch, 
         assert (g_s[k].double() - want).abs().max().item() <= 1e-4 * scale, k
 
 
+def test_opnet_fused_backward_falls_back_when_logits_carry_gradient(cuda_device, monkeypatch):
+    """The fused backward assumes no gradient on the who-to-track logits (the reference's training loss); when one
+    arrives the separate kernels run.  Both must agree with the oracle."""
+    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "1")
+    B, T, H1, H2 = 5, 21, 256, 512
+    boxes = torch.rand(B, T, 15, 6, generator=torch.Generator().manual_seed(2))
+    w = {"ih1": _rand((4 * H1, 90), 1, 1 / math.sqrt(H1)), "hh1": _rand((4 * H1, H1), 2, 1 / math.sqrt(H1)),
+         "pred": _rand((15, H1), 3, 1 / math.sqrt(H1)), "ih2": _rand((4 * H2, 6), 4, 1 / math.sqrt(H2)),
+         "hh2": _rand((4 * H2, H2), 5, 1 / math.sqrt(H2))}
+    dh2, dlg = _rand((B, T, H2), 6, 0.01), _rand((B, 15, T), 7, 0.01)
+    ws = {k: v.to(cuda_device).requires_grad_(True) for k, v in w.items()}
+    h2, logits = ops.opnet_trunk(boxes.to(cuda_device), ws["ih1"], ws["hh1"], ws["pred"], ws["ih2"], ws["hh2"])
+    torch.autograd.backward([h2, logits], [dh2.to(cuda_device), dlg.to(cuda_device)])
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    h1_r = oracle.lstm_layer(boxes.double().reshape(B, T, -1), wr["ih1"], wr["hh1"])
+    fb_r, lg_r = oracle.who_to_track(boxes.double(), h1_r, wr["pred"])
+    h2_r = oracle.lstm_layer(fb_r, wr["ih2"], wr["hh2"])
+    torch.autograd.backward([h2_r, lg_r.permute(0, 2, 1)], [dh2.double(), dlg.double()])
+    for k in w:
+        want = wr[k].grad
+        assert (ws[k].grad.cpu().double() - want).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item()), k
+
+
 def test_opnet_fused_forward_rejects_other_configs(cuda_device):
     lib = _lib.load()
     assert lib.opn_opnet_fwd(2, 2, 128, 512, *([None] * 16), 0, None) != 0
+    assert b"shipped OPNet config" in lib.opn_last_error()
+    assert lib.opn_opnet_bwd(2, 2, 256, 256, *([None] * 15), 0, None) != 0
     assert b"shipped OPNet config" in lib.opn_last_error()
 
 
