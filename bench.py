@@ -36,6 +36,7 @@ import torch
 OPNET_CFG = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
 B_PER_GPU, T, NOBJ, FEAT = 32, 300, 15, 6
 FUSED_FWD = os.environ.get("OPN_OPNET_FUSED", "1") not in ("0", "")   # the model's default forward path
+FUSED_BWD = FUSED_FWD and os.environ.get("OPN_OPNET_FUSED_BWD", "1") not in ("0", "")   # ... and backward path
 METRIC = "videos/sec OPNet fwd+bwd [B,T=300,N=15,h=256]"
 UNIT = "videos/s"
 
@@ -291,7 +292,27 @@ def run_ours(args):
         kern["opnet_fwd_fused"] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9,
                                    "us_per_step": ms * 1e3 / T,
                                    "matvec_tflops_fp32_equiv": 2.0 * rows * 4 * (H1 * H1 + H2 * H2) / (ms * 1e-3) / 1e12}
-        del bx, xp1, outs
+        # the fused OPNet backward (both reverse recurrences + who-to-track backward, one persistent kernel)
+        probs = torch.softmax(torch.randn(Bp, T, 15, **f32), -1)
+        g1 = torch.rand(Bp, T, 4 * H1, **f32); c1 = torch.randn(Bp, T, H1, **f32) * 0.5
+        g2 = torch.rand(Bp, T, 4 * H2, **f32); c2 = torch.randn(Bp, T, H2, **f32) * 0.5
+        dh2 = torch.randn(Bp, T, H2, **f32) * 0.01
+        dg1 = torch.empty(Bp, T, 4 * H1, **f32); dg2 = torch.empty(Bp, T, 4 * H2, **f32); dlg = torch.empty(Bp, T, 15, **f32)
+        wsb = torch.empty(lib.opn_opnet_bwd_workspace_bytes(Bp, T), dtype=torch.uint8, device=dev)
+
+        def fused_bwd():
+            _lib.check(lib.opn_opnet_bwd(Bp, T, H1, H2, bx.data_ptr(), probs.data_ptr(), w[0].data_ptr(), w[1].data_ptr(),
+                                         w[2].data_ptr(), w[3].data_ptr(), g1.data_ptr(), c1.data_ptr(), g2.data_ptr(),
+                                         c2.data_ptr(), dh2.data_ptr(), dg1.data_ptr(), dg2.data_ptr(), dlg.data_ptr(),
+                                         wsb.data_ptr(), wsb.numel(), s))
+
+        ms = time_alone(fused_bwd)
+        # read boxes, probs, the stash of both layers, dh2 and the four weight matrices; write dgates1, dgates2, d logits
+        alg = 4 * (rows * (90 + 15 + 5 * H1 + 5 * H2 + H2 + 4 * H1 + 4 * H2 + 15) + 4 * H1 * H1 + 15 * H1 + 4 * H2 * 6 + 4 * H2 * H2)
+        kern["opnet_bwd_fused"] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9,
+                                   "us_per_step": ms * 1e3 / T,
+                                   "matvec_tflops_fp32_equiv": 2.0 * rows * 4 * (H1 * H1 + H2 * H2) / (ms * 1e-3) / 1e12}
+        del bx, xp1, outs, probs, g1, c1, g2, c2, dh2, dg1, dg2
         for name, H in (("lstm_fwd_h512", H2), ("lstm_bwd_h512", H2), ("lstm_fwd_h256", H1), ("lstm_bwd_h256", H1)):
             xp = torch.randn(Bp, T, 4 * H, **f32) * 0.5
             whh = (torch.rand(4 * H, H, **f32) * 2 - 1) / (H ** 0.5)
@@ -319,10 +340,10 @@ def run_ours(args):
             kern[name] = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9,
                           "us_per_step": ms * 1e3 / T,
                           "matvec_tflops_fp32_equiv": 2.0 * rows * 4 * H * H / (ms * 1e-3) / 1e12}
-    # the step launches the fused forward and the two backward recurrences; the separate forward kernels are listed
-    # for reference (other model families use them)
-    in_step = ("opnet_fwd_fused", "lstm_bwd_h512", "lstm_bwd_h256") if FUSED_FWD else (
-        "lstm_fwd_h512", "lstm_bwd_h512", "lstm_fwd_h256", "lstm_bwd_h256")
+    # the step launches the fused forward and the fused backward; the stand-alone recurrences are listed for reference
+    # (other model families use them)
+    in_step = (("opnet_fwd_fused",) if FUSED_FWD else ("lstm_fwd_h512", "lstm_fwd_h256")) + (
+        ("opnet_bwd_fused",) if FUSED_BWD else ("lstm_bwd_h512", "lstm_bwd_h256"))
     for k in kern:
         kern[k]["in_step"] = k in in_step
     dom = max(in_step, key=lambda k: kern[k]["ms"])

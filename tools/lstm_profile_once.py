@@ -26,3 +26,15 @@ wsf = torch.empty(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, de
 _lib.check(lib.opn_opnet_fwd(B, T, H1, H2, bx.data_ptr(), xp1.data_ptr(), *[x.data_ptr() for x in w], *[o.data_ptr() for o in outs], wsf.data_ptr(), wsf.numel(), torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 print("done fused")
+# fused OPNet backward, once
+probs = torch.softmax(torch.randn(B, T, 15, **f32), -1)
+g1 = torch.rand(B, T, 4 * H1, **f32); c1 = torch.randn(B, T, H1, **f32) * 0.5
+g2 = torch.rand(B, T, 4 * H2, **f32); c2 = torch.randn(B, T, H2, **f32) * 0.5
+dh2 = torch.randn(B, T, H2, **f32) * 0.01
+dg1 = torch.empty(B, T, 4 * H1, **f32); dg2 = torch.empty(B, T, 4 * H2, **f32); dlg = torch.empty(B, T, 15, **f32)
+wsb = torch.empty(lib.opn_opnet_bwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+_lib.check(lib.opn_opnet_bwd(B, T, H1, H2, bx.data_ptr(), probs.data_ptr(), w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(), w[3].data_ptr(),
+                             g1.data_ptr(), c1.data_ptr(), g2.data_ptr(), c2.data_ptr(), dh2.data_ptr(), dg1.data_ptr(), dg2.data_ptr(), dlg.data_ptr(),
+                             wsb.data_ptr(), wsb.numel(), torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+print("done fused bwd")
