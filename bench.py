@@ -217,11 +217,11 @@ def run_ours(args):
         time.sleep(0.3)
 
     # untimed spin-up: the first process on a fresh box measured 24 % slow for its first seconds (clock ramp, lazy
-    # module loading); run the step for about two seconds before the W warm-up steps and the K timed ones
-    spin_end = time.time() + 2.0
-    while time.time() < spin_end:
+    # module loading); run the step a FIXED number of times (every rank must issue the same number of all-reduces)
+    # before the W warm-up steps and the K timed ones
+    for _ in range(400):
         step.forward_backward(boxes_d, labels_d)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
 
     # (1) device-resident inputs
     total_ms, launches, w0, w1 = timed(lambda: step.forward_backward(boxes_d, labels_d), args.steps, args.warmup)
