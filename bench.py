@@ -7,9 +7,11 @@ H1=256, H2=512), one process per GPU, gradients all-reduced once per step when N
 
 Prints ONE JSON line on rank 0 (contract in the task prompt):
   value     whole-job videos/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e       the same through objectpermanence_b200.training.TrainingStep with pinned HOST buffers
-            (H2D of boxes+labels and a D2H read of the loss inside the timed region)
-  roofline  the dominant kernel (the persistent LSTM2 backward recurrence) against measured HBM peak
+  e2e       the same through objectpermanence_b200.training.TrainingStep.pipelined with pinned HOST buffers
+            (H2D of boxes+labels on a copy stream and a D2H read of the loss inside the timed region; the host reads the
+            loss of the previous step, the last one is drained before the region closes)
+  roofline  the dominant kernel of the step (the fused OPNet backward or forward, whichever is longer, timed alone)
+            against the measured HBM peak; `kernels` lists every recurrence kernel with `in_step` marking what the step runs
   cpu_baseline  the oracle port of the reference path on the host cores, bounded sample
 `--impl reference` times only that CPU port (the reference is pure Python on PyTorch and is not
 present on the GPU box; oracle/opnet_oracle.py restates it and calls the same fused CPU LSTM
