@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
     // fragment word of this lane's row pair lr = ul*4 + 2*half, +1:  k-step lr>>4, r = lr&15
     const int lr_pair = ul * 4 + 2 * half;
     const int da_word = 4 * ((lr_pair >> 4) * 32 + bl * 4 + (((lr_pair & 15) & 7) >> 1)) + ((lr_pair & 15) >> 3);
+    // word offset of this thread's first published partial sum (m-tile warp*MPW, column g, video 2*tq) in a ring slot
+    const int pub_off = (((warp * MPW) * (U == 16 ? 1 : 2)) * kGroup * NS + slice) * U + g + (2 * tq) * (NS * U);
 
     float dc_carry = 0.0f, dh_rec = 0.0f;
     // stash of the step being processed (s*) and of the next one (n*): prefetched two steps ahead, the loads of a
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
 #pragma unroll
             for (int ks = 0; ks < KSB; ++ks) bf[ks] = dafrag_s[buf][ks * 32 + lane];
             const float inv0 = dainv_s[buf][2 * tq], inv1 = dainv_s[buf][2 * tq + 1];
+            uint32_t* pub = slot + pub_off;
 #pragma unroll
             for (int mi = 0; mi < MPW; ++mi) {
                 float dm[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
@@ -447,18 +450,17 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
                     mma_f16(ds, ahi[mi][ks], bf[ks].z, bf[ks].w);
                     mma_f16(ds, alo[mi][ks], bf[ks].x, bf[ks].y);
                 }
-                // D: (column kc, videos 2tq, 2tq+1), (column kc+8, same videos);
-                // column k belongs to consumer k / U, unit k % U: word [consumer][b][producer = slice][unit]
-                const int kc = (warp * MPW + mi) * 16 + g;
+                // D: (column kc, videos 2tq, 2tq+1), (column kc+8, same videos), kc = (warp*MPW + mi)*16 + g;
+                // column k belongs to consumer k / U, unit k % U: word [consumer][b][producer = slice][unit].
+                // U = 16: consumer warp*MPW + mi, unit g + 8*(q>>1);  U = 8: consumer 2*(warp*MPW + mi) + (q>>1), unit g.
+                // One base pointer per step, compile-time offsets, and no bounds check per word: videos past the end
+                // of the batch are stored too (zeros; nobody reads them) -- 12 -> 5 instructions per published word.
+                constexpr int kTileStride = (U == 16 ? 1 : 2) * kGroup * NS * U;   // words between consecutive m-tiles
+                constexpr int kHalfStride = (U == 16) ? 8 : kGroup * NS * U;       // words between columns kc and kc + 8
+                uint32_t* base = pub + mi * kTileStride;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = kc + 8 * (q >> 1), b = 2 * tq + (q & 1);
-                    if (b < nvalid) {
-                        const float val = (dm[q] + ds[q]) * ((q & 1) ? inv1 : inv0);
-                        st_flagged(slot + ((size_t)(k / U) * kGroup * NS + slice) * U + (k % U) + (size_t)b * NS * U, val,
-                                   par);
-                    }
-                }
+                for (int q = 0; q < 4; ++q)
+                    st_flagged(base + (q >> 1) * kHalfStride + (q & 1) * (NS * U), (dm[q] + ds[q]) * ((q & 1) ? inv1 : inv0), par);
             }
         }
 
