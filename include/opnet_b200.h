@@ -164,6 +164,12 @@ OPN_API int opn_layernorm_fwd(int64_t rows, int64_t D, const float* x, const flo
 /* backward: dx [rows,D] (gradient w.r.t. the sum x+res); dw, db [D] are accumulated (+=) */
 OPN_API int opn_layernorm_bwd(int64_t rows, int64_t D, const float* xhat, const float* rstd, const float* w, const float* dy,
                       float* dx, float* dw, float* db, void* stream);
+/* out[i] = keep(i) ? x[i] / (1 - p) : 0, in place allowed (out == x).  keep(i) is a pure function of (seed, offset, i):
+ * word i%4 of Philox4x32-10 block offset + i/4 under key `seed` is >= p * 2^32.  Forward and backward of a dropout
+ * site are the same call with the same (seed, offset); nothing is stashed.  One call consumes (n+3)/4 blocks of the
+ * offset space.  Replaces the four nn.Dropout(p=0.1) sites of nn.TransformerEncoderLayer in train mode
+ * (baselines/learned_models.py:166; statistically, not bit-wise: the mask generator is not PyTorch's). */
+OPN_API int opn_dropout(int64_t n, const float* x, float* out, float p, uint64_t seed, uint64_t offset, void* stream);
 /* out = a + b */
 OPN_API int opn_add(int64_t n, const float* a, const float* b, float* out, void* stream);
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_ulonglong, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # OPN_B200_LIB selects a development variant of the library (e.g. the phase-counter build); never a fallback
@@ -43,6 +43,7 @@ SIGNATURES = {
     "opn_layernorm_fwd": (c_int, [c_int64, c_int64, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
     "opn_layernorm_bwd": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "opn_add": (c_int, [c_int64, _P, _P, _P, _P]),
+    "opn_dropout": (c_int, [c_int64, _P, _P, c_float, c_uint64, c_uint64, _P]),
     "opn_loss_fwd_bwd": (c_int, [c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P]),
     "opn_adam_step": (c_int, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
     "opn_iou_eval": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kSkinnyThreads) rowdot_kernel(const float* __r
 // ---- colred ----------------------------------------------------------------------------------------------------
 // C[w, j] += alpha * sum_{k in chunk} S[k][w] * L[k][j];  element (w, j) of C at C[w*cs_w + j*cs_j].
 // Every thread owns 4 consecutive columns j (one 16-byte load per row of L) and 4*W accumulators.
-template <int W>
+template <int W, int U>
 __global__ void __launch_bounds__(kSkinnyThreads) colred_kernel(const float* __restrict__ S, long long lds,
                                                                 const float* __restrict__ L, long long ldl,
                                                                 float* __restrict__ C, long long cs_w, long long cs_j,
@@ -87,12 +87,12 @@ __global__ void __launch_bounds__(kSkinnyThreads) colred_kernel(const float* __r
         if (j < J) {
             const float* lp = L + (long long)k0 * ldl + j;
             int kk = 0;
-            for (; kk + 4 <= kc; kk += 4) {   // four rows in flight
-                float4 l[4];
+            for (; kk + U <= kc; kk += U) {   // U rows (16 bytes each per thread) in flight: the kernel is a pure stream
+                float4 l[U];                  // over L and ran at 1.5 TB/s with U = 4, one CTA per SM
 #pragma unroll
-                for (int u = 0; u < 4; ++u) l[u] = __ldg(reinterpret_cast<const float4*>(lp + (long long)(kk + u) * ldl));
+                for (int u = 0; u < U; ++u) l[u] = __ldg(reinterpret_cast<const float4*>(lp + (long long)(kk + u) * ldl));
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
                         const float sv = ss[kk + u][w];
@@ -192,14 +192,22 @@ int launch_colred(const float* S, long long lds, const float* L, long long ldl, 
         OPN_CUDA(cudaGetLastError());
         count_launch();
     }
+    static int legacy = -1;   // OPN_COLRED_LEGACY=1: four rows in flight, about one CTA per SM (the first version; kept for A/B)
+    if (legacy < 0) {
+        const char* e = getenv("OPN_COLRED_LEGACY");
+        legacy = (e && e[0] == '1') ? 1 : 0;
+    }
     const int gx = (J / 4 + kSkinnyThreads - 1) / kSkinnyThreads;
-    int splits = (148 * 2 + gx - 1) / gx;                 // about two CTAs per SM in total
+    int splits = (148 * (legacy ? 2 : 4) + gx - 1) / gx;   // up to four CTAs per SM in total (k_per_cta >= 64 caps it)
     int k_per_cta = (K + splits - 1) / splits;
     k_per_cta = (k_per_cta + 63) / 64 * 64;
     if (k_per_cta < 64) k_per_cta = 64;
     splits = (K + k_per_cta - 1) / k_per_cta;
-    colred_kernel<W><<<dim3((unsigned)gx, (unsigned)splits), kSkinnyThreads, 0, s>>>(S, lds, L, ldl, C, cs_w, cs_j, J, K,
-                                                                                      k_per_cta, alpha);
+    const dim3 grid((unsigned)gx, (unsigned)splits);
+    if (legacy)
+        colred_kernel<W, 4><<<grid, kSkinnyThreads, 0, s>>>(S, lds, L, ldl, C, cs_w, cs_j, J, K, k_per_cta, alpha);
+    else
+        colred_kernel<W, 8><<<grid, kSkinnyThreads, 0, s>>>(S, lds, L, ldl, C, cs_w, cs_j, J, K, k_per_cta, alpha);
     OPN_CUDA(cudaGetLastError());
     count_launch();
     return OPN_OK;

@@ -147,6 +147,49 @@ __global__ void add_kernel(long long n, const float* __restrict__ a, const float
         out[i] = a[i] + b[i];
 }
 
+// ---- dropout (train mode of nn.TransformerEncoderLayer, baselines/learned_models.py:166) ----
+// Counter-based mask: element i belongs to Philox4x32-10 block (offset + i/4), word i%4, key = seed; it is kept when
+// its word >= p * 2^32.  Nothing is stashed: the backward pass calls the same entry with the same (seed, offset).
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long ctr, unsigned long long seed) {
+    unsigned int c0 = (unsigned int)ctr, c1 = (unsigned int)(ctr >> 32), c2 = 0u, c3 = 0u;
+    unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__global__ void __launch_bounds__(256) dropout_kernel(long long n, const float* __restrict__ x, float* __restrict__ out,
+                                                      unsigned int threshold, float scale, unsigned long long seed,
+                                                      unsigned long long offset, int vec) {
+    const long long blocks = (n + 3) >> 2;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < blocks;
+         q += (long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(offset + (unsigned long long)q, seed);
+        const long long i = q << 2;
+        if (vec && i + 3 < n) {
+            float4 v = *reinterpret_cast<const float4*>(x + i);
+            v.x = r.x >= threshold ? v.x * scale : 0.0f;
+            v.y = r.y >= threshold ? v.y * scale : 0.0f;
+            v.z = r.z >= threshold ? v.z * scale : 0.0f;
+            v.w = r.w >= threshold ? v.w * scale : 0.0f;
+            *reinterpret_cast<float4*>(out + i) = v;
+        } else {
+            const unsigned int w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + j < n) out[i + j] = w[j] >= threshold ? x[i + j] * scale : 0.0f;
+        }
+    }
+}
+
 // column sums: grid.x covers columns (32 per block), grid.y splits rows; fp32 atomics
 __global__ void __launch_bounds__(256) colsum_kernel(long long rows, int cols, const float* __restrict__ x,
                                                      long long ld, float* __restrict__ out) {
@@ -402,6 +445,21 @@ extern "C" int opn_add(int64_t n, const float* a, const float* b, float* out, vo
     OPN_CHECK_ARG(n >= 0 && a && b && out, "add: bad argument");
     if (n == 0) return OPN_OK;
     add_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(n, a, b, out);
+    OPN_CUDA(cudaGetLastError());
+    count_launch();
+    return OPN_OK;
+}
+
+extern "C" int opn_dropout(int64_t n, const float* x, float* out, float p, uint64_t seed, uint64_t offset, void* stream) {
+    OPN_CHECK_ARG(n >= 0 && x && out, "dropout: bad argument");
+    OPN_CHECK_ARG(p >= 0.0f && p < 1.0f, "dropout: p = %g outside [0, 1)", (double)p);
+    if (n == 0) return OPN_OK;
+    double t = (double)p * 4294967296.0;
+    const unsigned int threshold = t >= 4294967295.0 ? 4294967295u : (unsigned int)t;
+    const float scale = 1.0f / (1.0f - p);
+    const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    dropout_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(n, x, out, threshold, scale, seed, offset,
+                                                                             vec);
     OPN_CUDA(cudaGetLastError());
     count_launch();
     return OPN_OK;

@@ -20,6 +20,7 @@ from . import ops
 
 FFN_DIM = 2048   # nn.TransformerEncoderLayer default dim_feedforward (learned_models.py:166)
 LN_EPS = 1e-5
+DROPOUT_P = 0.1  # nn.TransformerEncoderLayer default dropout (learned_models.py:166)
 
 
 class LstmWeights(nn.Module):
@@ -176,12 +177,16 @@ class _NormWeights(nn.Module):
 
 class EncoderLayer(nn.Module):
     """Post-norm encoder layer with nn.TransformerEncoderLayer's parameter names, evaluated on one
-    sequence of S rows.  Dropout (p=0.1 in the reference's train mode) is not applied: parity
-    with the reference is defined in eval() mode."""
+    sequence of S rows.  In train mode the layer's four dropout sites (attention weights, dropout1 after the
+    attention block, dropout inside the feed-forward block, dropout2 after it; p = 0.1, the PyTorch default the
+    reference relies on) are applied with the library's counter-based mask (ops.dropout): the same distribution
+    as the reference, not the same random stream, so parity with the reference is defined in eval() mode or at
+    `dropout_p = 0`."""
 
-    def __init__(self, d: int, nhead: int):
+    def __init__(self, d: int, nhead: int, dropout_p: float = DROPOUT_P):
         super().__init__()
         self.nhead = nhead
+        self.dropout_p = dropout_p
         self.self_attn = _SelfAttnWeights(d)
         self.linear1 = LinearWeights(d, FFN_DIM, bias=True)
         self.linear2 = LinearWeights(FFN_DIM, d, bias=True)
@@ -189,10 +194,18 @@ class EncoderLayer(nn.Module):
         self.norm2 = _NormWeights(d)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # x [S, D]
+        p = self.dropout_p if self.training else 0.0
         qkv = ops.linear(x, self.self_attn.in_proj_weight, self.self_attn.in_proj_bias)
-        attn = self.self_attn.out_proj(ops.self_attention(qkv, self.nhead))
+        if p > 0.0:
+            S = x.shape[0]
+            seed, offset = ops.dropout_stream.take(self.nhead * (4 * ((S * S + 3) // 4)))
+            attended = ops.self_attention(qkv, self.nhead, p, seed, offset)
+        else:
+            attended = ops.self_attention(qkv, self.nhead)
+        attn = ops.dropout(self.self_attn.out_proj(attended), p, self.training)
         x = ops.add_layer_norm(x, attn, self.norm1.weight, self.norm1.bias, LN_EPS)
-        ff = self.linear2(self.linear1(x, relu=True))
+        ff = self.linear2(ops.dropout(self.linear1(x, relu=True), p, self.training))
+        ff = ops.dropout(ff, p, self.training)
         return ops.add_layer_norm(x, ff, self.norm2.weight, self.norm2.bias, LN_EPS)
 
 

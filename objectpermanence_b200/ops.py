@@ -77,9 +77,48 @@ def _lstm_check(ws: torch.Tensor, what: str) -> None:
         _lib.check(rc, what)
 
 
+def dropout_(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, offset: int) -> None:
+    """out = x * keep / (1 - p) with the counter-based mask of opn_dropout (out may be x)."""
+    rc = _lib.load().opn_dropout(x.numel(), x.data_ptr(), out.data_ptr(), p, seed, offset, _stream())
+    _lib.check(rc, "opn_dropout")
+
+
+class DropoutStream:
+    """Hands out (seed, offset) pairs for dropout sites.  Every site draws a fresh 62-bit Philox key from torch's
+    default CPU generator (a host-side draw, no device work), so masks follow torch.manual_seed() the way the
+    reference's nn.Dropout masks do, and no two sites share mask words."""
+
+    def take(self, n_elements: int) -> Tuple[int, int]:
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()), 0
+
+
+dropout_stream = DropoutStream()
+
+
 # ------------------------------------------------------------------------------------------
 # autograd functions
 # ------------------------------------------------------------------------------------------
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout of the encoder layer in train mode (dropout / dropout1 / dropout2 of
+    nn.TransformerEncoderLayer, baselines/learned_models.py:166).  The mask is regenerated in backward."""
+
+    @staticmethod
+    def forward(ctx, x, p: float, seed: int, offset: int):
+        _require_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        dropout_(x, y, p, seed, offset)
+        ctx.args = (p, seed, offset)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        dropout_(dy, dx, *ctx.args)
+        return dx, None, None, None
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T (+ bias) (ReLU).  x [..., K] contiguous, W [N, K].  nn.Linear call sites of
     baselines/learned_models.py (:30,:33,:67,:69,:70,:102,:130,:133,:167,:172)."""
@@ -386,9 +425,30 @@ class OPNetTrunkFn(torch.autograd.Function):
                                    dgates2.data_ptr(), dl.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
             _lib.check(rc, "opn_opnet_bwd")
             _lstm_check(ws, "opn_opnet_bwd")
+            x1 = boxes.reshape(B, T, -1)
+            if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "1") not in ("0", "") and all(need[1:]):
+                # The five weight-gradient contractions are independent of each other and none fills the GPU (pre-pass,
+                # 16-64 output tiles, split-K): LSTM2's stay on the main stream, LSTM1's and dW_pred run beside them
+                # (2.61 -> 2.58 ms per step, tools/step_ab.py; OPN_OPNET_WGRAD_OVERLAP=0 runs them in line).
+                main, side = torch.cuda.current_stream(), _side_stream(dev)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, x1, hs1, w_ih1, w_hh1, True, True)
+                    dw_pred = _wtt_weight_grad(hs1, dl)
+                dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, True, True)
+                for t_ in (dgates1, boxes, hs1, dl):
+                    t_.record_stream(side)
+                done = torch.cuda.Event()
+                done.record(side)
+                main.wait_event(done)
+                for t_ in (dw_ih1, dw_hh1, dw_pred):
+                    t_.record_stream(main)
+                return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
             dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, need[4], need[5])
             dw_pred = _wtt_weight_grad(hs1, dl) if need[3] else None
-            dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, boxes.reshape(B, T, -1), hs1, w_ih1, w_hh1, need[1], need[2])
+            dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, x1, hs1, w_ih1, w_hh1, need[1], need[2])
             return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
         dgates2 = _lstm_recurrence_backward(w_hh2, gates2, cells2, dhs2)
         dfb = torch.empty_like(fb)
@@ -470,7 +530,7 @@ class SelfAttentionFn(torch.autograd.Function):
     materialised per head in HBM ([S,S] fp32; 369 MB at S = 9600) and kept for the backward pass."""
 
     @staticmethod
-    def forward(ctx, qkv, nhead: int):
+    def forward(ctx, qkv, nhead: int, p_drop: float = 0.0, seed: int = 0, offset: int = 0):
         _require_cuda(qkv)
         qkv = qkv.contiguous()
         S, D3 = qkv.shape
@@ -481,23 +541,32 @@ class SelfAttentionFn(torch.autograd.Function):
         lib = _lib.load()
         ctx_out = torch.empty(S, D, device=dev, dtype=torch.float32)
         probs = torch.empty(nhead, S, S, device=dev, dtype=torch.float32)
+        # train mode: nn.MultiheadAttention drops attention weights after the softmax; the dropped copy feeds P V
+        # (and dV in backward), the softmax backward needs the undropped one
+        dropped = torch.empty_like(probs) if p_drop > 0.0 else None
+        head_blocks = (S * S + 3) // 4
         for h in range(nhead):
             p = probs[h]
             # scores = q_h k_h^T
             sgemm(qkv, qkv, p, trans_a=False, trans_b=True, M=S, N=S, K=d, lda=D3, ldb=D3, ldc=S, a_off=h * d,
                   b_off=D + h * d)
             _lib.check(lib.opn_softmax_rows(S, S, p.data_ptr(), S, scale, _stream()), "opn_softmax_rows")
+            if dropped is not None:
+                dropout_(p, dropped[h], p_drop, seed, offset + h * head_blocks)
+                p = dropped[h]
             # ctx_h = P v_h
             sgemm(p, qkv, ctx_out, trans_a=False, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D3, ldc=D,
                   b_off=2 * D + h * d, c_off=h * d)
-        ctx.save_for_backward(qkv, probs)
+        ctx.save_for_backward(qkv, probs, dropped)
         ctx.nhead = nhead
+        ctx.drop = (p_drop, seed, offset)
         return ctx_out
 
     @staticmethod
     def backward(ctx, dctx):
-        qkv, probs = ctx.saved_tensors
+        qkv, probs, dropped = ctx.saved_tensors
         nhead = ctx.nhead
+        p_drop, seed, offset = ctx.drop
         S, D3 = qkv.shape
         D = D3 // 3
         d = D // nhead
@@ -507,14 +576,17 @@ class SelfAttentionFn(torch.autograd.Function):
         dctx = dctx.contiguous()
         dqkv = torch.empty_like(qkv)
         dp = torch.empty(S, S, device=dev, dtype=torch.float32)
+        head_blocks = (S * S + 3) // 4
         for h in range(nhead):
             p = probs[h]
-            # dV_h = P^T dctx_h
-            sgemm(p, dctx, dqkv, trans_a=True, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D, ldc=D3, b_off=h * d,
-                  c_off=2 * D + h * d)
+            # dV_h = P^T dctx_h  (the dropped P in train mode)
+            sgemm(p if dropped is None else dropped[h], dctx, dqkv, trans_a=True, trans_b=False, M=S, N=d, K=S, lda=S,
+                  ldb=D, ldc=D3, b_off=h * d, c_off=2 * D + h * d)
             # dP = dctx_h V_h^T
             sgemm(dctx, qkv, dp, trans_a=False, trans_b=True, M=S, N=S, K=d, lda=D, ldb=D3, ldc=S, a_off=h * d,
                   b_off=2 * D + h * d)
+            if dropped is not None:
+                dropout_(dp, dp, p_drop, seed, offset + h * head_blocks)
             # dS = scale * P * (dP - rowsum(P dP))
             _lib.check(lib.opn_softmax_rows_bwd(S, S, p.data_ptr(), dp.data_ptr(), S, scale, _stream()),
                        "opn_softmax_rows_bwd")
@@ -523,7 +595,7 @@ class SelfAttentionFn(torch.autograd.Function):
                   c_off=h * d)
             sgemm(dp, qkv, dqkv, trans_a=True, trans_b=False, M=S, N=d, K=S, lda=S, ldb=D3, ldc=D3, b_off=h * d,
                   c_off=D + h * d)
-        return dqkv, None
+        return dqkv, None, None, None, None
 
 
 class TrainingLossFn(torch.autograd.Function):
@@ -587,8 +659,17 @@ def add_layer_norm(x, res, weight, bias, eps: float = 1e-5):
     return AddLayerNormFn.apply(x, res, weight, bias, eps)
 
 
-def self_attention(qkv, nhead: int):
-    return SelfAttentionFn.apply(qkv, nhead)
+def self_attention(qkv, nhead: int, p_drop: float = 0.0, seed: int = 0, offset: int = 0):
+    """p_drop > 0: attention-weight dropout with the mask of (seed, offset); one head consumes (S*S+3)//4 blocks."""
+    return SelfAttentionFn.apply(qkv, nhead, p_drop, seed, offset)
+
+
+def dropout(x, p: float, training: bool = True):
+    """F.dropout with the library's counter-based mask; identity in eval mode or at p = 0."""
+    if not training or p <= 0.0:
+        return x
+    seed, offset = dropout_stream.take(x.numel())
+    return DropoutFn.apply(x, p, seed, offset)
 
 
 def slot_linear_relu(boxes, weight, slot: int = 0):

@@ -235,13 +235,15 @@ def test_lstm_unsupported_hidden_size(cuda_device):
 
 
 # ---- fused OPNet forward ----------------------------------------------------------------------
-@pytest.mark.parametrize("bwd", ["fused", "separate"])
+@pytest.mark.parametrize("bwd", ["fused", "fused_inline", "separate"])
 @pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (11, 37), (32, 64), (70, 9), (8, 300)])
 def test_opnet_fused_forward_matches_separate_kernels(cuda_device, monkeypatch, B, T, bwd):
     """LSTM1 + who-to-track + LSTM2 as one persistent kernel (and the mirror-image fused backward: both reverse
     recurrences + the who-to-track backward) against the chain of separate kernels and the fp64 oracle: outputs and the
     gradients of all five weight matrices through every path."""
-    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "1" if bwd == "fused" else "0")
+    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "0" if bwd == "separate" else "1")
+    # after the fused backward the weight-gradient contractions run on two streams (default) or in line
+    monkeypatch.setenv("OPN_OPNET_WGRAD_OVERLAP", "0" if bwd == "fused_inline" else "1")
     H1, H2 = 256, 512
     boxes = torch.rand(B, T, 15, 6, generator=torch.Generator().manual_seed(5 + B)) * (torch.rand(B, T, 15, 1) > 0.3)
     w = {"ih1": _rand((4 * H1, 90), 1, 1 / math.sqrt(H1)), "hh1": _rand((4 * H1, H1), 2, 1 / math.sqrt(H1)),
@@ -357,6 +359,67 @@ def test_self_attention(cuda_device, S, D, nhead):
     ref.backward(dctx.double())
     qg = qkv.to(cuda_device).requires_grad_(True)
     out = ops.self_attention(qg, nhead)
+    out.backward(dctx.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
+    assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4
+
+
+# ---- dropout (train mode of the encoder layer) ------------------------------------------------
+@pytest.mark.parametrize("n,p,seed,offset", [(1, 0.1, 1, 0), (4, 0.1, 7, 3), (1027, 0.1, 1234, 0), (65536, 0.5, 2 ** 40 + 5, 2 ** 33),
+                                              (100003, 0.0, 9, 11), (300 * 300 + 1, 0.9, 3, 12345)])
+def test_dropout_mask_is_the_specified_philox_stream(cuda_device, n, p, seed, offset):
+    from oracle import dropout_mask
+    x = _rand((n,), 70) + 2.0           # no zeros: a zero in the output is a dropped element
+    want = dropout_mask.dropout(x.numpy(), p, seed, offset)
+    xd = x.to(cuda_device)
+    out = torch.full_like(xd, float("nan"))
+    ops.dropout_(xd, out, p, seed, offset)
+    assert torch.equal(out.cpu(), torch.from_numpy(want))
+    # unaligned views take the scalar path and see the same stream; in place is allowed
+    if n > 8:
+        buf = torch.zeros(n + 1, device=cuda_device)
+        buf[1:] = xd
+        ops.dropout_(buf[1:], buf[1:], p, seed, offset)
+        assert torch.equal(buf[1:].cpu(), torch.from_numpy(want))
+
+
+def test_dropout_keep_rate_and_backward(cuda_device):
+    torch.manual_seed(5)
+    x = (_rand((512, 2048), 71) + 2.0).to(cuda_device).requires_grad_(True)
+    y = ops.dropout(x, 0.1, training=True)
+    kept = (y != 0)
+    assert abs(kept.float().mean().item() - 0.9) < 2e-3
+    assert (y[kept] - x.detach()[kept] / 0.9).abs().max().item() < 1e-5
+    w = _rand((512, 2048), 72).to(cuda_device)
+    (y * w).sum().backward()
+    assert (x.grad - torch.where(kept, w / 0.9, torch.zeros_like(w))).abs().max().item() < 1e-6
+    # consecutive sites never share mask words; eval mode / p = 0 are the identity (same tensor, no launch)
+    y2 = ops.dropout(x, 0.1, training=True)
+    assert not torch.equal(y2 != 0, kept)
+    assert ops.dropout(x, 0.1, training=False) is x and ops.dropout(x, 0.0, training=True) is x
+    # the stream restarts with torch.manual_seed
+    torch.manual_seed(5)
+    assert torch.equal(ops.dropout(x, 0.1, training=True), y)
+
+
+@pytest.mark.parametrize("S,D,nhead", [(48, 32, 2), (301, 64, 2)])
+def test_self_attention_with_weight_dropout(cuda_device, S, D, nhead):
+    """nn.MultiheadAttention drops attention weights after the softmax; checked against plain fp64 math with the
+    mask of the same (seed, offset) taken from the oracle's restatement of the generator."""
+    from oracle import dropout_mask
+    p_drop, seed, offset = 0.1, 99, 1000
+    qkv, dctx = _rand((S, 3 * D), 53), _rand((S, D), 54)
+    qr = qkv.double().requires_grad_(True)
+    d = D // nhead
+    q, k, v = [z.reshape(S, nhead, d).permute(1, 0, 2) for z in (qr[:, :D], qr[:, D:2 * D], qr[:, 2 * D:])]
+    blocks = (S * S + 3) // 4
+    keep = torch.stack([torch.from_numpy(dropout_mask.keep_mask(S * S, p_drop, seed, offset + h * blocks)).reshape(S, S)
+                        for h in range(nhead)])
+    probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1) * keep.double() / (1.0 - p_drop)
+    ref = (probs @ v).permute(1, 0, 2).reshape(S, D)
+    ref.backward(dctx.double())
+    qg = qkv.to(cuda_device).requires_grad_(True)
+    out = ops.self_attention(qg, nhead, p_drop, seed, offset)
     out.backward(dctx.to(cuda_device))
     assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
     assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4

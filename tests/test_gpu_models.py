@@ -23,7 +23,8 @@ BBOX_TOL = 1e-4
 def _run_module(model_name, config, params, boxes, labels, mask, device):
     model = ModelsFactory.get_model(model_name, config)
     model.load_state_dict(params)
-    model = model.to(device).train()
+    # parity with the reference is defined without dropout (oracle/make_golden.py records the transformer in eval())
+    model = model.to(device).train(not model_name.startswith("transformer"))
     out = model(boxes.to(device))
     y, logits = out if isinstance(out, tuple) else (out, None)
     loss3 = ops.training_loss(y, labels.to(device), mask.to(device), model_name.endswith("no_labels"))
@@ -131,6 +132,46 @@ def test_transformer_lstm_shipped_config_small_batch(cuda_device):
     cfg = {"boxes_features_dim": 256, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2,
            "lstm_hidden_dim": 512}
     _oracle_vs_module("transformer_lstm", cfg, 2, 300, cuda_device, seed=8, grad_tol=2e-3)
+
+
+def test_transformer_lstm_train_mode_applies_dropout(cuda_device):
+    """The reference's encoder layers carry nn.Dropout(p=0.1) at four sites (baselines/learned_models.py:166).  The
+    mask stream is this library's own (ops.dropout), so the check is behavioural: train mode differs from eval mode
+    by a dropout-sized amount, is reproducible under torch.manual_seed, gives finite gradients for every parameter,
+    and `dropout_p = 0` reproduces eval mode exactly."""
+    cfg = {"boxes_features_dim": 64, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2,
+           "lstm_hidden_dim": 64}
+    boxes_np, labels_np, _ = make_batch(3, 40, 5, seed=77)
+    boxes, labels = torch.from_numpy(boxes_np).to(cuda_device), torch.from_numpy(labels_np).to(cuda_device)
+    torch.manual_seed(0)
+    model = ModelsFactory.get_model("transformer_lstm", cfg).to(cuda_device)
+
+    def run(train):
+        model.train(train)
+        model.zero_grad(set_to_none=True)
+        y = model(boxes)
+        ops.training_loss(y, labels)[0].backward()
+        return y.detach().clone(), {k: v.grad.detach().clone() for k, v in model.named_parameters()}
+
+    def close(a, b, rel=1e-5):      # split-K contractions sum with fp32 atomics: equal up to summation order
+        return (a - b).abs().max().item() <= rel * max(1e-6, b.abs().max().item())
+
+    y_eval, g_eval = run(False)
+    torch.manual_seed(11)
+    y_a, g_a = run(True)
+    torch.manual_seed(11)
+    y_b, g_b = run(True)
+    y_c, _ = run(True)            # the stream has advanced: other masks
+    assert close(y_a, y_b) and all(close(g_a[k], g_b[k]) for k in g_a)
+    scale = y_eval.abs().max().item()
+    assert (y_a - y_c).abs().max().item() > 1e-3 * scale
+    diff = (y_a - y_eval).abs().max().item()
+    assert 1e-3 * scale < diff < 0.5 * scale + 0.05, (diff, scale)
+    assert all(torch.isfinite(g).all() and g.abs().max() > 0 for g in g_a.values())
+    for layer in model.attention_encoder.layers:
+        layer.dropout_p = 0.0
+    y_p0, g_p0 = run(True)
+    assert close(y_p0, y_eval) and all(close(g_p0[k], g_eval[k]) for k in g_eval)
 
 
 def test_transformer_lstm_tensor_core_attention(cuda_device):

@@ -56,6 +56,22 @@ def test_iou_metric_matches_reference_analyzer():
     assert abs(oracle.mean_iou(blob["pred"], blob["gt"]) - float(blob["mean_iou"])) < 1e-12
 
 
+def test_dropout_mask_restatement_matches_philox_known_answers():
+    """Random123's published known-answer vectors for Philox4x32-10 pin the generator opn_dropout specifies."""
+    from oracle.dropout_mask import keep_mask, philox4x32_10
+    kats = [([0, 0, 0, 0], (0, 0), [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+            ([0xffffffff] * 4, (0xffffffff, 0xffffffff), [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+            ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0),
+             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kats:
+        got = philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert [int(v) for v in got] == want
+    m = keep_mask(1_000_003, 0.1, 1234, 77)
+    assert m.shape == (1_000_003,) and abs(m.mean() - 0.9) < 1e-3
+    assert keep_mask(1000, 0.0, 1, 0).all()
+    assert np.array_equal(keep_mask(64, 0.3, 5, 4), keep_mask(80, 0.3, 5, 0)[16:])   # offset = 4-element blocks
+
+
 def test_unknown_model_name():
     with pytest.raises(AttributeError):
         oracle.family_of("opnet_v2")

@@ -18,12 +18,15 @@ def step():
     loss = ops.training_loss(y, labels, None, False)
     loss[0].backward()
     return loss
-step(); torch.cuda.synchronize()
-n0 = _lib.launch_count()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); 
-for _ in range(3): loss = step()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 3
-print(f"transformer_lstm [B={B},T=300] fwd+loss+bwd: {ms:.2f} ms/step = {B / ms * 1e3:.1f} videos/s, loss {loss[0].item():.5f}, "
-      f"kernels/step {(_lib.launch_count() - n0) // 3}, peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
+for mode in (True, False):      # train mode applies the encoder's four dropout sites (p = 0.1); eval mode is the parity mode
+    model.train(mode)
+    step(); torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): loss = step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"transformer_lstm [B={B},T=300] {'train (dropout 0.1)' if mode else 'eval (no dropout)'} fwd+loss+bwd: {ms:.2f} ms/step = "
+          f"{B / ms * 1e3:.1f} videos/s, loss {loss[0].item():.5f}, kernels/step {(_lib.launch_count() - n0) // 3}, "
+          f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB", flush=True)
