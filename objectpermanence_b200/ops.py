@@ -24,6 +24,33 @@ def set_debug_sync(flag: bool) -> None:
     _DEBUG_SYNC = bool(flag)
 
 
+class LaunchTimer:
+    """Optional CUDA-event brackets around the two persistent OPNet launches, on the stream they are launched on.
+    bench.py installs one for its timed region so that the roofline figure of the dominant kernel comes from the
+    launches of the measured steps themselves; without one nothing is recorded."""
+
+    def __init__(self):
+        self.pairs = {}
+
+    def bracket(self, name: str):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.pairs.setdefault(name, []).append((e0, e1))
+        return e0, e1
+
+    def mean_ms(self, name: str) -> Optional[float]:
+        """Average duration of the recorded launches (call after a device synchronise)."""
+        pairs = self.pairs.get(name)
+        return sum(a.elapsed_time(b) for a, b in pairs) / len(pairs) if pairs else None
+
+
+_launch_timer: Optional[LaunchTimer] = None
+
+
+def set_launch_timer(timer: Optional[LaunchTimer]) -> None:
+    global _launch_timer
+    _launch_timer = timer
+
+
 def _require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if t is None:
@@ -390,10 +417,15 @@ class OPNetTrunkFn(torch.autograd.Function):
             gates2 = torch.empty(B, T, 4 * H2, **f32)
             cells2 = torch.empty(B, T, H2, **f32)
         ws = torch.empty(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+        timed = _launch_timer.bracket("opnet_fwd_fused") if _launch_timer is not None else None
+        if timed:
+            timed[0].record()
         rc = lib.opn_opnet_fwd(B, T, H1, H2, boxes.data_ptr(), xproj1.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
                                w_ih2.data_ptr(), w_hh2.data_ptr(), hs1.data_ptr(), _ptr(gates1), _ptr(cells1),
                                logits.data_ptr(), probs.data_ptr(), fb.data_ptr(), hs2.data_ptr(), _ptr(gates2),
                                _ptr(cells2), ws.data_ptr(), ws.numel(), _stream())
+        if timed:
+            timed[1].record()
         _lib.check(rc, "opn_opnet_fwd")
         _lstm_check(ws, "opn_opnet_fwd")
         if need_grad:
@@ -419,10 +451,16 @@ class OPNetTrunkFn(torch.autograd.Function):
             dgates1 = torch.empty(B, T, 4 * H1, device=dev, dtype=torch.float32)
             dl = torch.empty(B, T, 15, device=dev, dtype=torch.float32)
             ws = torch.empty(lib.opn_opnet_bwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+            dhs2 = dhs2.contiguous()
+            timed = _launch_timer.bracket("opnet_bwd_fused") if _launch_timer is not None else None
+            if timed:
+                timed[0].record()
             rc = lib.opn_opnet_bwd(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
                                    w_ih2.data_ptr(), w_hh2.data_ptr(), gates1.data_ptr(), cells1.data_ptr(),
-                                   gates2.data_ptr(), cells2.data_ptr(), dhs2.contiguous().data_ptr(), dgates1.data_ptr(),
+                                   gates2.data_ptr(), cells2.data_ptr(), dhs2.data_ptr(), dgates1.data_ptr(),
                                    dgates2.data_ptr(), dl.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            if timed:
+                timed[1].record()
             _lib.check(rc, "opn_opnet_bwd")
             _lstm_check(ws, "opn_opnet_bwd")
             x1 = boxes.reshape(B, T, -1)
@@ -598,28 +636,35 @@ class SelfAttentionFn(torch.autograd.Function):
         return dqkv, None, None, None, None
 
 
+def loss_and_grad(y, labels, mask=None, no_labels: bool = False):
+    """The loss of baselines/training_main.py:192-210 and d total / dy in one launch, outside autograd:
+    (3-vector (total, prediction, consistency), dy [B,T,4]).  `y.backward(dy)` continues into the model."""
+    _require_cuda(y, labels)
+    y = y.detach().contiguous()
+    labels = labels.contiguous()
+    B, T, C = y.shape
+    if C != 4:
+        raise RuntimeError("training loss expects [B,T,4] predictions")
+    m = None
+    if no_labels:
+        if mask is None:
+            raise RuntimeError("*_no_labels models need the visibility mask")
+        m = mask.to(torch.uint8).contiguous()
+    out = torch.empty(3, device=y.device, dtype=torch.float32)
+    dy = torch.empty_like(y)
+    rc = _lib.load().opn_loss_fwd_bwd(B, T, y.data_ptr(), labels.data_ptr(), _ptr(m), int(no_labels),
+                                      out.data_ptr(), dy.data_ptr(), _stream())
+    _lib.check(rc, "opn_loss_fwd_bwd")
+    return out, dy
+
+
 class TrainingLossFn(torch.autograd.Function):
-    """The loss of baselines/training_main.py:192-210 and its gradient in one launch.
-    Returns a 3-vector (total, prediction, consistency); only `total` carries gradient."""
+    """loss_and_grad as an autograd node: returns the 3-vector (total, prediction, consistency); only `total`
+    carries gradient."""
 
     @staticmethod
     def forward(ctx, y, labels, mask, no_labels: bool):
-        _require_cuda(y, labels)
-        y = y.contiguous()
-        labels = labels.contiguous()
-        B, T, C = y.shape
-        if C != 4:
-            raise RuntimeError("training loss expects [B,T,4] predictions")
-        m = None
-        if no_labels:
-            if mask is None:
-                raise RuntimeError("*_no_labels models need the visibility mask")
-            m = mask.to(torch.uint8).contiguous()
-        out = torch.empty(3, device=y.device, dtype=torch.float32)
-        dy = torch.empty_like(y)
-        rc = _lib.load().opn_loss_fwd_bwd(B, T, y.data_ptr(), labels.data_ptr(), _ptr(m), int(no_labels),
-                                          out.data_ptr(), dy.data_ptr(), _stream())
-        _lib.check(rc, "opn_loss_fwd_bwd")
+        out, dy = loss_and_grad(y, labels, mask, no_labels)
         ctx.save_for_backward(dy)
         return out
 

@@ -54,13 +54,15 @@ class TrainingStep:
             p.grad = None
         out = self.model(boxes)
         y = out[0] if _is_double_output(self.model_name) else out
-        loss3 = ops.training_loss(y, labels, mask, _is_no_labels(self.model_name))
-        loss3[0].backward()
+        # the loss launch also writes d total / dy: seed the backward pass with it directly (loss3[0].backward() would
+        # add autograd's own fill / select / multiply kernels in front of it)
+        loss3, dy = ops.loss_and_grad(y, labels, mask, _is_no_labels(self.model_name))
+        y.backward(dy)
         if self.reducer is not None:
             self.reducer.reduce()
         if self.optimizer is not None:
             self.optimizer.step()
-        return loss3.detach()
+        return loss3
 
     def __call__(self, boxes: torch.Tensor, labels: torch.Tensor, mask: Optional[torch.Tensor] = None):
         """End-to-end step from HOST buffers: async H2D of the inputs, forward_backward, and a

@@ -67,6 +67,28 @@ def test_fused_adam_trains_like_torch_adam(cuda_device):
     d.load_state_dict({k: v.cpu() for k, v in b.state_dict().items()})
 
 
+def test_training_step_gradients_equal_the_autograd_loss_path(cuda_device):
+    """TrainingStep seeds the backward pass with the dy the loss launch wrote (ops.loss_and_grad + y.backward(dy));
+    the gradients must be those of `ops.training_loss(...)[0].backward()`, for the labelled and the *_no_labels loss."""
+    from objectpermanence_b200 import ops
+    from objectpermanence_b200.training import TrainingStep
+    cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    for name in ("opnet", "opnet_no_labels"):
+        torch.manual_seed(1)
+        model = ModelsFactory.get_model(name, cfg).to(cuda_device)
+        b, l, m = make_batch(5, 20, 6, seed=60)
+        boxes, labels, mask = [torch.from_numpy(t).to(cuda_device) for t in (b, l, m)]
+        loss_a = TrainingStep(model, name).forward_backward(boxes, labels, mask)
+        grads_a = {k: p.grad.clone() for k, p in model.named_parameters()}
+        model.zero_grad(set_to_none=True)
+        y, _ = model(boxes)
+        loss_b = ops.training_loss(y, labels, mask, name.endswith("no_labels"))
+        loss_b[0].backward()
+        assert torch.equal(loss_a, loss_b.detach())
+        for k, p in model.named_parameters():
+            assert (grads_a[k] - p.grad).abs().max().item() <= 1e-5 * max(1e-6, p.grad.abs().max().item()), k  # atomics reorder sums
+
+
 def test_iou_eval_matches_reference_analyzer_fixture(cuda_device):
     blob = np.load(f"{GOLDEN}/iou_metric.npz")
     video, _, _, frame = iou_eval(torch.from_numpy(blob["pred"]).to(cuda_device), torch.from_numpy(blob["gt"]).to(cuda_device),
