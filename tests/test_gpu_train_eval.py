@@ -84,7 +84,7 @@ def test_training_step_gradients_equal_the_autograd_loss_path(cuda_device):
         y, _ = model(boxes)
         loss_b = ops.training_loss(y, labels, mask, name.endswith("no_labels"))
         loss_b[0].backward()
-        assert torch.equal(loss_a, loss_b.detach())
+        assert (loss_a - loss_b.detach()).abs().max().item() <= 1e-6     # the loss is summed with fp32 atomics
         for k, p in model.named_parameters():
             assert (grads_a[k] - p.grad).abs().max().item() <= 1e-5 * max(1e-6, p.grad.abs().max().item()), k  # atomics reorder sums
 
