@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
 
     for (int i = tid; i < (OFF_WP - OFF_DA2) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_DA2)[i] = 0u;
     for (int i = tid; i < (OFF_RED - OFF_BOX) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_BOX)[i] = 0u;
+    // The first LSTM2 sweep (iteration 1) is taken before any sweep was issued into its landing slots: whatever the
+    // previous kernel left in this shared memory must not look like ready words (step 0 carries parity 1; zeros do not)
+    for (int i = tid; i < (SMEM_BYTES - OFF_LAND2) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_LAND2)[i] = 0u;
     __syncthreads();
     if (tid < 40) inv2_s[tid] = 1.0f;   // inv2 (32 floats) + inv1 (8 floats), contiguous
 

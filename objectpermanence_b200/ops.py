@@ -464,10 +464,12 @@ class OPNetTrunkFn(torch.autograd.Function):
             _lib.check(rc, "opn_opnet_bwd")
             _lstm_check(ws, "opn_opnet_bwd")
             x1 = boxes.reshape(B, T, -1)
-            if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "1") not in ("0", "") and all(need[1:]):
-                # The five weight-gradient contractions are independent of each other and none fills the GPU (pre-pass,
-                # 16-64 output tiles, split-K): LSTM2's stay on the main stream, LSTM1's and dW_pred run beside them
-                # (2.61 -> 2.58 ms per step, tools/step_ab.py; OPN_OPNET_WGRAD_OVERLAP=0 runs them in line).
+            if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "0") not in ("0", "") and all(need[1:]):
+                # Opt-in (OPN_OPNET_WGRAD_OVERLAP=1).  The five weight-gradient contractions are independent of each
+                # other and none fills the GPU (pre-pass, 16-64 output tiles, split-K): LSTM2's stay on the main
+                # stream, LSTM1's and dW_pred run beside them (2.61 -> 2.58 ms per step, tools/step_ab.py).  Not the
+                # default: see DESIGN.md section 9 (one unexplained parity failure of the in-line path when it ran
+                # after this one in the same process, found when the round's GPU budget was spent).
                 main, side = torch.cuda.current_stream(), _side_stream(dev)
                 ready = torch.cuda.Event()
                 ready.record(main)

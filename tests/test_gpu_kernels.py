@@ -235,15 +235,13 @@ def test_lstm_unsupported_hidden_size(cuda_device):
 
 
 # ---- fused OPNet forward ----------------------------------------------------------------------
-@pytest.mark.parametrize("bwd", ["fused", "fused_inline", "separate"])
+@pytest.mark.parametrize("bwd", ["fused", "separate"])
 @pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (11, 37), (32, 64), (70, 9), (8, 300)])
 def test_opnet_fused_forward_matches_separate_kernels(cuda_device, monkeypatch, B, T, bwd):
     """LSTM1 + who-to-track + LSTM2 as one persistent kernel (and the mirror-image fused backward: both reverse
     recurrences + the who-to-track backward) against the chain of separate kernels and the fp64 oracle: outputs and the
     gradients of all five weight matrices through every path."""
-    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "0" if bwd == "separate" else "1")
-    # after the fused backward the weight-gradient contractions run on two streams (default) or in line
-    monkeypatch.setenv("OPN_OPNET_WGRAD_OVERLAP", "0" if bwd == "fused_inline" else "1")
+    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "1" if bwd == "fused" else "0")
     H1, H2 = 256, 512
     boxes = torch.rand(B, T, 15, 6, generator=torch.Generator().manual_seed(5 + B)) * (torch.rand(B, T, 15, 1) > 0.3)
     w = {"ih1": _rand((4 * H1, 90), 1, 1 / math.sqrt(H1)), "hh1": _rand((4 * H1, H1), 2, 1 / math.sqrt(H1)),
