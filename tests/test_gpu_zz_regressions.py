@@ -1,0 +1,49 @@
+"""GPU: regression cases added after the round-1 GPU budget was spent.  They run LAST (file name) so that the long
+validated order of the other GPU tests is unchanged, and are xfail(strict=False) until they have been seen on a GPU."""
+import math
+
+import pytest
+import torch
+
+from objectpermanence_b200 import ops
+from oracle import opnet_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * scale).float()
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: not yet run on a GPU (DESIGN.md section 9)")
+@pytest.mark.parametrize("T", [38, 39])
+def test_opnet_fused_backward_back_to_back_launches(cuda_device, monkeypatch, T):
+    """The fused backward takes its first LSTM2 sweep (iteration 1) from shared-memory landing slots that no sweep was
+    issued into yet; step 0 carries parity 1, and for T = 2, 3 (mod 4) the LAST sweep of a launch also carries parity 1,
+    so what a launch leaves in shared memory would pass as ready words in the next launch on the same SM.  The kernel
+    zeroes the slots at its start; this runs the backward three times on one graph (nothing with a large shared-memory
+    footprint in between at this size) and compares every launch with the fp64 oracle."""
+    monkeypatch.setenv("OPN_OPNET_FUSED_BWD", "1")
+    monkeypatch.setenv("OPN_OPNET_WGRAD_OVERLAP", "0")
+    B, H1, H2 = 5, 256, 512
+    boxes = torch.rand(B, T, 15, 6, generator=torch.Generator().manual_seed(40 + T))
+    w = {"ih1": _rand((4 * H1, 90), 1, 1 / math.sqrt(H1)), "hh1": _rand((4 * H1, H1), 2, 1 / math.sqrt(H1)),
+         "pred": _rand((15, H1), 3, 1 / math.sqrt(H1)), "ih2": _rand((4 * H2, 6), 4, 1 / math.sqrt(H2)),
+         "hh2": _rand((4 * H2, H2), 5, 1 / math.sqrt(H2))}
+    dh2 = _rand((B, T, H2), 6, 0.01)
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    h1_r = oracle.lstm_layer(boxes.double().reshape(B, T, -1), wr["ih1"], wr["hh1"])
+    fb_r, _ = oracle.who_to_track(boxes.double(), h1_r, wr["pred"])
+    oracle.lstm_layer(fb_r, wr["ih2"], wr["hh2"]).backward(dh2.double())
+    ws = {k: v.to(cuda_device).requires_grad_(True) for k, v in w.items()}
+    h2, _ = ops.opnet_trunk(boxes.to(cuda_device), ws["ih1"], ws["hh1"], ws["pred"], ws["ih2"], ws["hh2"])
+    dh2_d = dh2.to(cuda_device)
+    for launch in range(3):
+        for v in ws.values():
+            v.grad = None
+        h2.backward(dh2_d, retain_graph=True)
+        for k in w:
+            want = wr[k].grad
+            err = (ws[k].grad.cpu().double() - want).abs().max().item()
+            assert err <= 2e-4 * max(1e-3, want.abs().max().item()), (launch, k, err)
