@@ -119,3 +119,25 @@ def test_fused_adam_and_iou_eval_have_no_cpu_path():
         FusedAdam([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
     with pytest.raises(RuntimeError, match="no CPU path"):
         iou_eval(torch.zeros(1, 2, 4), torch.zeros(1, 2, 4))
+
+
+def test_dropout_sites_follow_torch_manual_seed_and_have_no_cpu_path():
+    """Host side of the encoder's train-mode dropout: every site draws its Philox key from torch's CPU generator (so a
+    run is reproducible under torch.manual_seed and no two sites share a key); eval mode / p = 0 are the identity and
+    never touch the library; train mode on a CPU tensor raises (no CPU path)."""
+    from objectpermanence_b200 import ops
+    torch.manual_seed(123)
+    a, b = ops.dropout_stream.take(1000), ops.dropout_stream.take(1000)
+    torch.manual_seed(123)
+    c = ops.dropout_stream.take(7)
+    assert a == c and a != b and a[1] == 0 and 0 <= a[0] < 2 ** 62
+    x = torch.ones(4, 8)
+    assert ops.dropout(x, 0.1, training=False) is x and ops.dropout(x, 0.0, training=True) is x
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.dropout(x, 0.1, training=True)
+    # the transformer variant keeps the reference's default p = 0.1 and switches with train() / eval()
+    cfg = {"boxes_features_dim": 32, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 1,
+           "lstm_hidden_dim": 32}
+    model = ModelsFactory.get_model("transformer_lstm", cfg)
+    assert all(layer.dropout_p == 0.1 for layer in model.attention_encoder.layers)
+    assert model.training and not model.eval().training
