@@ -1,5 +1,5 @@
-"""GPU: regression cases added after the round-1 GPU budget was spent.  They run LAST (file name) so that the long
-validated order of the other GPU tests is unchanged, and are xfail(strict=False) until they have been seen on a GPU."""
+"""GPU: regression cases added at the very end of round 1.  They run LAST (file name) so that the long validated order
+of the other GPU tests is unchanged (seen green on a B200 in the round's last call, gpurun_out c20)."""
 import math
 
 import pytest
@@ -16,7 +16,6 @@ def _rand(shape, seed, scale=1.0):
     return ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * scale).float()
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: not yet run on a GPU (DESIGN.md section 9)")
 @pytest.mark.parametrize("T", [38, 39])
 def test_opnet_fused_backward_back_to_back_launches(cuda_device, monkeypatch, T):
     """The fused backward takes its first LSTM2 sweep (iteration 1) from shared-memory landing slots that no sweep was
