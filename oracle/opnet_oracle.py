@@ -31,7 +31,9 @@ algorithms restated here, explicitly and without calling ``nn.LSTM`` /
   layer_norm_eps=1e-5, *sequence-first* layout: the reference hands it a
   ``(B*T, 15, D)`` tensor, so the attended axis is ``B*T`` and the 15 object slots are
   the independent "batch" axis -- learned_models.py:166,183-185).  Dropout is the
-  identity here: parity is defined in ``eval()`` mode.
+  identity unless the caller pins the masks of the layer's four nn.Dropout sites
+  (``encoder_layer(..., drop=...)``): parity with the reference is defined in ``eval()``
+  mode, parity of the library's own train mode against pinned masks.
 
 Parity pinning
 --------------
@@ -145,10 +147,18 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tenso
     return (x - mu) / torch.sqrt(var + LN_EPS) * w + b
 
 
-def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int) -> torch.Tensor:
+def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int, drop=None) -> torch.Tensor:
     """One post-norm encoder layer over x [S, N, D] (sequence-first, N independent
-    columns), eval mode.  Restates nn.TransformerEncoderLayer as built at
-    learned_models.py:166 (d_model=D, nhead, defaults otherwise)."""
+    columns).  Restates nn.TransformerEncoderLayer as built at
+    learned_models.py:166 (d_model=D, nhead, defaults otherwise).
+
+    ``drop`` = None is eval mode.  Train mode: ``drop(site, tensor) -> tensor`` is called at the layer's four
+    nn.Dropout sites in execution order -- "<prefix>.attn" (attention weights [N,nhead,S,S], after the softmax),
+    "<prefix>.dropout1" (the attention block's output [S,N,D]), "<prefix>.dropout" (after the ReLU, [S,N,2048]),
+    "<prefix>.dropout2" ([S,N,D]) -- and applies whatever mask the caller pins (tests: the counter-based mask of
+    oracle/dropout_mask.py; PyTorch's own random stream cannot be pinned)."""
+    if drop is None:
+        drop = lambda site, t: t
     S, N, D = x.shape
     dh = D // nhead
     qkv = x @ p[f"{prefix}.self_attn.in_proj_weight"].t() + p[f"{prefix}.self_attn.in_proj_bias"]
@@ -159,12 +169,12 @@ def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int) -> torch.
 
     q, k, v = heads(q), heads(k), heads(v)
     scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
-    attn = torch.softmax(scores, dim=-1) @ v                      # [N,nhead,S,dh]
+    attn = drop(f"{prefix}.attn", torch.softmax(scores, dim=-1)) @ v   # [N,nhead,S,dh]
     attn = attn.permute(2, 0, 1, 3).reshape(S, N, D)
     attn = attn @ p[f"{prefix}.self_attn.out_proj.weight"].t() + p[f"{prefix}.self_attn.out_proj.bias"]
-    x = layer_norm(x + attn, p[f"{prefix}.norm1.weight"], p[f"{prefix}.norm1.bias"])
-    ff = torch.relu(x @ p[f"{prefix}.linear1.weight"].t() + p[f"{prefix}.linear1.bias"])
-    ff = ff @ p[f"{prefix}.linear2.weight"].t() + p[f"{prefix}.linear2.bias"]
+    x = layer_norm(x + drop(f"{prefix}.dropout1", attn), p[f"{prefix}.norm1.weight"], p[f"{prefix}.norm1.bias"])
+    ff = drop(f"{prefix}.dropout", torch.relu(x @ p[f"{prefix}.linear1.weight"].t() + p[f"{prefix}.linear1.bias"]))
+    ff = drop(f"{prefix}.dropout2", ff @ p[f"{prefix}.linear2.weight"].t() + p[f"{prefix}.linear2.bias"])
     return layer_norm(x + ff, p[f"{prefix}.norm2.weight"], p[f"{prefix}.norm2.bias"])
 
 
@@ -209,8 +219,8 @@ def non_linear_lstm_forward(p: Params, x: torch.Tensor, fast: bool = False):
 
 
 def transformer_lstm_forward(p: Params, x: torch.Tensor, config: Dict[str, int], fast: bool = False,
-                             all_slots: bool = False):
-    """learned_models.py:174-197 in eval mode.
+                             all_slots: bool = False, drop=None):
+    """learned_models.py:174-197; eval mode unless ``drop`` pins the dropout masks (see encoder_layer).
 
     ``all_slots=True`` evaluates the encoder on the full (B*T, 15, D) tensor exactly as
     the reference does; the default evaluates slot 0 only, which is the same function:
@@ -223,7 +233,7 @@ def transformer_lstm_forward(p: Params, x: torch.Tensor, config: Dict[str, int],
     if not all_slots:
         seq = seq[:, :1, :]
     for i in range(config["num_attention_layers"]):
-        seq = encoder_layer(seq, p, f"attention_encoder.layers.{i}", nhead)
+        seq = encoder_layer(seq, p, f"attention_encoder.layers.{i}", nhead, drop)
     snitch = seq[:, 0, :].reshape(B, T, -1)
     h = lstm_stack(snitch, p, "video_LSTM", config["num_lstm_layers"], fast)
     return h @ p["predictions_layer.weight"].t()
@@ -338,10 +348,11 @@ def training_loss(y: torch.Tensor, labels: torch.Tensor, mask: Optional[torch.Te
 
 def loss_and_grads(model_name: str, p: Params, boxes: torch.Tensor, labels: torch.Tensor,
                    config: Optional[Dict[str, int]] = None, dtype=torch.float64, fast: bool = False,
-                   mask: Optional[torch.Tensor] = None):
-    """Forward + L1 loss + autograd backward in ``dtype``.  Returns (y, logits|None, loss, grads)."""
+                   mask: Optional[torch.Tensor] = None, **kw):
+    """Forward + L1 loss + autograd backward in ``dtype``.  Returns (y, logits|None, loss, grads).
+    Keyword arguments go to the model's forward (transformer_lstm: all_slots, drop)."""
     q = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in p.items()}
-    out = forward(model_name, q, boxes.to(dtype), config, fast)
+    out = forward(model_name, q, boxes.to(dtype), config, fast, **kw)
     y, logits = out if isinstance(out, tuple) else (out, None)
     loss = training_loss(y, labels.to(dtype), None if mask is None else mask.to(dtype),
                          no_labels=model_name.endswith("no_labels"))

@@ -46,3 +46,55 @@ def test_opnet_fused_backward_back_to_back_launches(cuda_device, monkeypatch, T)
             want = wr[k].grad
             err = (ws[k].grad.cpu().double() - want).abs().max().item()
             assert err <= 2e-4 * max(1e-3, want.abs().max().item()), (launch, k, err)
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: not yet run on a GPU")
+def test_transformer_lstm_train_mode_matches_the_oracle_with_pinned_masks(cuda_device, monkeypatch):
+    """Train mode end to end: the (seed, offset) of every dropout site of the run is recorded, the oracle applies the
+    restated Philox masks (oracle/dropout_mask.py) at the same sites, and outputs and every gradient must agree."""
+    from objectpermanence_b200.models_factory import ModelsFactory
+    from objectpermanence_b200.synthetic import make_batch
+    from oracle import dropout_mask
+
+    class Recorder(ops.DropoutStream):
+        def __init__(self):
+            self.log = []
+
+        def take(self, n):
+            key = super().take(n)
+            self.log.append(key)
+            return key
+
+    rec = Recorder()
+    monkeypatch.setattr(ops, "dropout_stream", rec)
+    cfg = {"boxes_features_dim": 32, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2,
+           "lstm_hidden_dim": 32}
+    B, T, p_drop = 2, 12, 0.1
+    boxes_np, labels_np, _ = make_batch(B, T, 5, seed=91)
+    boxes, labels = torch.from_numpy(boxes_np), torch.from_numpy(labels_np)
+    params = oracle.init_params("transformer_lstm", cfg, seed=4)
+    model = ModelsFactory.get_model("transformer_lstm", cfg)
+    model.load_state_dict(params)
+    model = model.to(cuda_device).train()
+    torch.manual_seed(17)
+    y = model(boxes.to(cuda_device))
+    ops.training_loss(y, labels.to(cuda_device))[0].backward()
+    assert len(rec.log) == 4 * cfg["num_attention_layers"]
+    keys = iter(rec.log)
+
+    def drop(site, t):
+        seed, offset = next(keys)
+        if site.endswith(".attn"):          # [1, nhead, S, S]: head h consumes its own (S*S+3)//4 Philox blocks
+            S = t.shape[-1]
+            blocks = (S * S + 3) // 4
+            keep = torch.stack([torch.from_numpy(dropout_mask.keep_mask(S * S, p_drop, seed, offset + h * blocks)).reshape(S, S)
+                                for h in range(t.shape[1])])[None]
+        else:
+            keep = torch.from_numpy(dropout_mask.keep_mask(t.numel(), p_drop, seed, offset)).reshape(t.shape)
+        return t * keep.to(t.dtype) / (1.0 - p_drop)
+
+    y_ref, _, _, g_ref = oracle.loss_and_grads("transformer_lstm", params, boxes, labels, cfg, dtype=torch.float64, drop=drop)
+    assert (y.detach().cpu().double() - y_ref).abs().max().item() <= 1e-4
+    for k, v in model.named_parameters():
+        err = (v.grad.cpu().double() - g_ref[k]).abs().max().item()
+        assert err <= 2e-3 * max(1e-3, g_ref[k].abs().max().item()), (k, err)

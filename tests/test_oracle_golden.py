@@ -75,3 +75,40 @@ def test_dropout_mask_restatement_matches_philox_known_answers():
 def test_unknown_model_name():
     with pytest.raises(AttributeError):
         oracle.family_of("opnet_v2")
+
+
+def test_oracle_dropout_sites_match_the_torch_encoder_layer():
+    """Train mode of the restated encoder layer: the three nn.Dropout modules of nn.TransformerEncoderLayer are
+    replaced by fixed masks in a real torch layer and the same masks are pinned in the oracle (the attention-weight
+    dropout lives inside scaled_dot_product_attention and cannot be pinned there: it is switched off on both sides and
+    covered by the kernel-level test against plain fp64 math)."""
+    torch.manual_seed(3)
+    S, N, D, nhead, p_drop = 10, 3, 32, 2, 0.1
+    layer = torch.nn.TransformerEncoderLayer(d_model=D, nhead=nhead).double().train()
+    layer.self_attn.dropout = 0.0
+    masks = {"dropout1": (torch.rand(S, N, D) >= p_drop).double() / (1 - p_drop),
+             "dropout": (torch.rand(S, N, 2048) >= p_drop).double() / (1 - p_drop),
+             "dropout2": (torch.rand(S, N, D) >= p_drop).double() / (1 - p_drop)}
+
+    class Fixed(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, t):
+            return t * self.m
+
+    layer.dropout1, layer.dropout, layer.dropout2 = Fixed(masks["dropout1"]), Fixed(masks["dropout"]), Fixed(masks["dropout2"])
+    x = torch.randn(S, N, D, dtype=torch.float64)
+    want = layer(x)
+    params = {f"L.{k}": v.detach() for k, v in layer.state_dict().items()}
+    seen = []
+
+    def drop(site, t):
+        seen.append(site)
+        name = site.rsplit(".", 1)[1]
+        return t if name == "attn" else t * masks[name]
+
+    got = oracle.encoder_layer(x, params, "L", nhead, drop)
+    assert seen == ["L.attn", "L.dropout1", "L.dropout", "L.dropout2"]
+    assert (got - want).abs().max().item() < 1e-12
