@@ -99,6 +99,14 @@ OPN_API int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, con
  * info[0..2] if info != NULL).  For tests and debugging. */
 OPN_API int opn_lstm_status(const void* workspace, uint32_t* info);
 
+/* Sticky status page.  `device_page`: >= 4096 zeroed bytes of device memory owned by the caller, registered for the
+ * CURRENT device (NULL unregisters).  While one is registered the persistent kernels (opn_lstm_*, opn_opnet_*) report
+ * time-outs into it instead of into the head of their per-launch workspace: word 0 = code (0 = fine), words 1..3 =
+ * step / CTA / thread.  The word is never cleared by the library, so the caller can read it wherever it synchronises
+ * anyway (e.g. together with the loss of a training step, as objectpermanence_b200.training does) and must zero it after
+ * reporting; while it is non-zero later launches give up at their first slow wait.  opn_lstm_status accepts the page. */
+OPN_API int opn_set_status_page(void* device_page);
+
 /* ---- OPNet "who to track" stage ---------------------------------------------------
  * forward (baselines/learned_models.py:40-43,50):
  *   logits = hs1 * w_pred^T            [B,T,15]

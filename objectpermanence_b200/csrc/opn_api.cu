@@ -16,6 +16,19 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Sticky status page (opn_set_status_page): when the caller registers one for a device, the persistent kernels report
+// time-outs there instead of into the head of their (per-launch, memset) workspace, so the word survives until the host
+// reads it where it synchronises anyway (training step, inference) and later launches bail out at once instead of each
+// waiting out its own time-out.
+static void* g_status_page[64] = {nullptr};
+
+unsigned int* status_page_or(void* workspace_head) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_status_page[dev])
+        return static_cast<unsigned int*>(g_status_page[dev]);
+    return static_cast<unsigned int*>(workspace_head);
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return OPN_ERR_CUDA;
@@ -28,6 +41,14 @@ extern "C" int opn_version(void) { return 100; /* 0.1.0 */ }
 extern "C" const char* opn_last_error(void) { return opn::g_error; }
 
 extern "C" unsigned long long opn_launch_count(void) { return opn::g_launch_count; }
+
+extern "C" int opn_set_status_page(void* device_page) {
+    int dev = 0;
+    OPN_CUDA(cudaGetDevice(&dev));
+    OPN_CHECK_ARG(dev >= 0 && dev < 64, "set_status_page: device ordinal %d out of range", dev);
+    opn::g_status_page[dev] = device_page;   // NULL: back to the workspace head
+    return OPN_OK;
+}
 
 extern "C" int opn_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;

@@ -11,6 +11,8 @@ namespace opn {
 // ---- host-side error plumbing ------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+// the status words of a persistent launch: the registered sticky page of the current device, else the workspace head
+unsigned int* status_page_or(void* workspace_head);
 
 #define OPN_CHECK_ARG(cond, ...)                 \
     do {                                         \

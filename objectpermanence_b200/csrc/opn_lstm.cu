@@ -604,7 +604,7 @@ extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj,
     p.gates = gates;
     p.cells = cells;
     p.ring = reinterpret_cast<uint32_t*>(ws + l.fwd_ring_off);
-    p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
+    p.status = status_page_or(ws + l.status_off);
     p.B = (int)B;
     p.T = (int)T;
     p.group_offset = 0;
@@ -642,7 +642,7 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     p.dh_out = dh_out;
     p.dgates = dgates;
     p.ring = reinterpret_cast<uint32_t*>(ws + l.bwd_ring_off);
-    p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
+    p.status = status_page_or(ws + l.status_off);
     p.B = (int)B;
     p.T = (int)T;
     p.group_offset = 0;

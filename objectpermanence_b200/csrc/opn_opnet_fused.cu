@@ -677,7 +677,7 @@ extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.cells2 = cells2;
     p.ring1 = reinterpret_cast<uint32_t*>(ws + l.ring1_off);
     p.ring2 = reinterpret_cast<uint32_t*>(ws + l.ring2_off);
-    p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
+    p.status = status_page_or(ws + l.status_off);
     p.B = (int)B;
     p.T = (int)T;
     p.group_offset = 0;

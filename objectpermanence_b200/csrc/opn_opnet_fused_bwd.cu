@@ -146,7 +146,14 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
     for (int i = tid; i < (OFF_RED - OFF_BOX) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_BOX)[i] = 0u;
     // The first LSTM2 sweep (iteration 1) is taken before any sweep was issued into its landing slots: whatever the
     // previous kernel left in this shared memory must not look like ready words (step 0 carries parity 1; zeros do not)
+    // (round-2 root cause of the [B=11,T=37] dW_ih2 failure: before this line existed, leftovers of the previous kernel on
+    // this SM with LSB = 1 were summed as the partial products of step 0.  -DOPN_POISON_LANDING reproduces that on purpose:
+    // tools/gpu_call_r2_03.sh, profiles/r02_landing_slot_root_cause.log)
+#ifdef OPN_POISON_LANDING
+    for (int i = tid; i < (SMEM_BYTES - OFF_LAND2) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_LAND2)[i] = 0x3A83126Fu;  // 1e-3f, LSB 1
+#else
     for (int i = tid; i < (SMEM_BYTES - OFF_LAND2) / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_LAND2)[i] = 0u;
+#endif
     __syncthreads();
     if (tid < 40) inv2_s[tid] = 1.0f;   // inv2 (32 floats) + inv1 (8 floats), contiguous
 
@@ -651,7 +658,7 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.ring2 = reinterpret_cast<uint32_t*>(ws + l.ring2_off);
     p.ring1 = reinterpret_cast<uint32_t*>(ws + l.ring1_off);
     p.ringf = reinterpret_cast<uint32_t*>(ws + l.ringf_off);
-    p.status = reinterpret_cast<unsigned int*>(ws + l.status_off);
+    p.status = status_page_or(ws + l.status_off);
     p.B = (int)B, p.T = (int)T;
     p.group_offset = 0, p.n_slices = NS;
     return launch_ring(opnet_bwd_fused_kernel, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");

@@ -82,6 +82,7 @@ def inference_and_iou_comp(model_name: str, model: torch.nn.Module, compute_devi
     video = torch.cat(video_means).cpu().tolist()         # the only device->host copies of the pass
     masked = torch.cat(masked_means).cpu().tolist() if masked_means else []
     average_loss = float(loss_sum.item()) / n_seen
+    ops.check_status(compute_device, "evaluation pass")   # the copies above synchronised: a timed-out recurrence raises here
     mean_iou = _nanmean(video)
     containment = _nanmean(masked) if masked else float("nan")
     return average_loss, mean_iou, containment

@@ -56,7 +56,9 @@ def predict_pixel_boxes(model_name: str, model: torch.nn.Module, device: torch.d
             n += len(video_names)
     if n == 0:
         return indices, np.zeros((0, 0, 4), np.int32), np.zeros((0, 0, 4), np.int32)
-    return indices, torch.cat(preds).cpu().numpy(), torch.cat(labs).cpu().numpy()
+    out_p, out_l = torch.cat(preds).cpu().numpy(), torch.cat(labs).cpu().numpy()
+    ops.check_status(device, "inference pass")   # the copies above synchronised: a timed-out recurrence raises here
+    return indices, out_p, out_l
 
 
 def write_bb_predictions(video_path: str, predictions_dir: str, boxes) -> Path:

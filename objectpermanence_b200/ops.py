@@ -8,7 +8,6 @@ CPU path -- CPU tensors raise.
 from __future__ import annotations
 
 import os
-from ctypes import c_uint32
 from typing import Optional, Tuple
 
 import torch
@@ -61,6 +60,10 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
                 "inputs to a B200 (`.to('cuda')`).")
         if t.dtype != torch.float32:
             raise RuntimeError(f"objectpermanence_b200 expects float32 tensors, got {t.dtype}")
+    for t in tensors:
+        if t is not None:
+            status_page(t.device)   # registered before the first persistent launch on this device
+            break
 
 
 def _stream() -> int:
@@ -97,11 +100,46 @@ def _lstm_workspace(B: int, T: int, H: int, device) -> torch.Tensor:
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
-def _lstm_check(ws: torch.Tensor, what: str) -> None:
+_status_pages = {}
+
+
+def status_page(device) -> torch.Tensor:
+    """The sticky status page of `device` (int32[1024], registered with the library on first use): the persistent
+    kernels report inter-CTA time-outs there (word 0 = code, 1..3 = step / CTA / thread).  Callers that synchronise
+    anyway (TrainingStep, inference, evaluation) copy its first 4 words along and hand them to `raise_if_failed`."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    page = _status_pages.get(idx)
+    if page is None:
+        page = torch.zeros(1024, dtype=torch.int32, device=torch.device("cuda", idx))
+        with torch.cuda.device(idx):
+            _lib.check(_lib.load().opn_set_status_page(page.data_ptr()), "opn_set_status_page")
+        _status_pages[idx] = page
+    return page
+
+
+def raise_if_failed(words, device, what: str = "persistent kernel") -> None:
+    """`words`: the first 4 status words on the HOST (after the copy has completed).  Clears the page and raises
+    OpnError(OPN_ERR_TIMEOUT) when a wait expired; outputs of the affected launches are garbage."""
+    code = int(words[0])
+    if code != 0:
+        detail = (int(words[1]), int(words[2]), int(words[3]))
+        status_page(device).zero_()
+        raise _lib.OpnError(f"libopnet_b200 {what} failed (code {_lib.OPN_ERR_TIMEOUT}): persistent LSTM kernel timed out "
+                            f"(status {code}, step {detail[0]}, cta {detail[1]}, thread {detail[2]}); the results of "
+                            "this step are invalid")
+
+
+def check_status(device, what: str = "persistent kernel") -> None:
+    """Blocking form: synchronise the current stream and check the status page of `device`."""
+    page = status_page(device)
+    words = page[:4].cpu()      # stream-ordered copy + host synchronisation
+    raise_if_failed(words, device, what)
+
+
+def _lstm_check(device, what: str) -> None:
     if _DEBUG_SYNC:
-        info = (c_uint32 * 3)()
-        rc = _lib.load().opn_lstm_status(ws.data_ptr(), info)
-        _lib.check(rc, what)
+        check_status(device, what)
 
 
 def dropout_(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, offset: int) -> None:
@@ -226,7 +264,7 @@ class LstmLayerFn(torch.autograd.Function):
     kernels plus the time-parallel input projection / gradient contractions."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh):
+    def forward(ctx, x, w_ih, w_hh, stash: bool = True):
         _require_cuda(x, w_ih, w_hh)
         x = x.contiguous()
         w_ih = w_ih.contiguous()
@@ -238,7 +276,9 @@ class LstmLayerFn(torch.autograd.Function):
         xproj = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
         sgemm(x, w_ih, xproj, trans_a=False, trans_b=True, M=B * T, N=4 * H, K=I, lda=I, ldb=I, ldc=4 * H)
         hs = torch.empty(B, T, H, device=dev, dtype=torch.float32)
-        need_grad = any(ctx.needs_input_grad)  # all False under torch.no_grad(): inference skips the stash
+        # `stash` comes from the front-end (lstm_layer): needs_input_grad mirrors requires_grad whatever the grad mode,
+        # and grad mode is always off inside Function.forward, so torch.no_grad() has to be seen by the caller
+        need_grad = stash and any(ctx.needs_input_grad)
         gates = cells = None
         if need_grad:
             gates = torch.empty(B, T, 4 * H, device=dev, dtype=torch.float32)
@@ -247,7 +287,7 @@ class LstmLayerFn(torch.autograd.Function):
         rc = lib.opn_lstm_fwd(B, T, H, xproj.data_ptr(), w_hh.data_ptr(), hs.data_ptr(), _ptr(gates), _ptr(cells),
                               ws.data_ptr(), ws.numel(), _stream())
         _lib.check(rc, "opn_lstm_fwd")
-        _lstm_check(ws, "opn_lstm_fwd")
+        _lstm_check(dev, "opn_lstm_fwd")
         if need_grad:
             ctx.save_for_backward(x, w_ih, w_hh, hs, gates, cells)
         return hs
@@ -255,7 +295,7 @@ class LstmLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dhs):
         x, w_ih, w_hh, hs, gates, cells = ctx.saved_tensors
-        return _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, ctx.needs_input_grad)
+        return _lstm_backward(x, w_ih, w_hh, hs, gates, cells, dhs, ctx.needs_input_grad) + (None,)
 
 
 def _lstm_recurrence_backward(w_hh, gates, cells, dhs):
@@ -269,7 +309,7 @@ def _lstm_recurrence_backward(w_hh, gates, cells, dhs):
     rc = lib.opn_lstm_bwd(B, T, H, w_hh.data_ptr(), gates.data_ptr(), cells.data_ptr(), dhs.data_ptr(),
                           dgates.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "opn_lstm_bwd")
-    _lstm_check(ws, "opn_lstm_bwd")
+    _lstm_check(gates.device, "opn_lstm_bwd")
     return dgates
 
 
@@ -391,7 +431,7 @@ class OPNetTrunkFn(torch.autograd.Function):
     time-parallel weight-gradient contractions."""
 
     @staticmethod
-    def forward(ctx, boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2):
+    def forward(ctx, boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2, stash: bool = True):
         _require_cuda(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2)
         boxes = boxes.contiguous()
         w_ih1, w_hh1, w_pred, w_ih2, w_hh2 = [w.contiguous() for w in (w_ih1, w_hh1, w_pred, w_ih2, w_hh2)]
@@ -403,7 +443,7 @@ class OPNetTrunkFn(torch.autograd.Function):
         xproj1 = torch.empty(B, T, 4 * H1, **f32)
         sgemm(boxes, w_ih1, xproj1, trans_a=False, trans_b=True, M=B * T, N=4 * H1, K=NO * F, lda=NO * F, ldb=NO * F,
               ldc=4 * H1)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = stash and any(ctx.needs_input_grad)   # see LstmLayerFn.forward
         ctx.set_materialize_grads(False)   # backward sees None (not zeros) when an output carries no gradient
         hs1 = torch.empty(B, T, H1, **f32)
         hs2 = torch.empty(B, T, H2, **f32)
@@ -427,7 +467,7 @@ class OPNetTrunkFn(torch.autograd.Function):
         if timed:
             timed[1].record()
         _lib.check(rc, "opn_opnet_fwd")
-        _lstm_check(ws, "opn_opnet_fwd")
+        _lstm_check(dev, "opn_opnet_fwd")
         if need_grad:
             ctx.save_for_backward(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2, hs1, gates1, cells1, probs, fb, hs2,
                                   gates2, cells2)
@@ -462,14 +502,12 @@ class OPNetTrunkFn(torch.autograd.Function):
             if timed:
                 timed[1].record()
             _lib.check(rc, "opn_opnet_bwd")
-            _lstm_check(ws, "opn_opnet_bwd")
+            _lstm_check(dev, "opn_opnet_bwd")
             x1 = boxes.reshape(B, T, -1)
-            if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "0") not in ("0", "") and all(need[1:]):
-                # Opt-in (OPN_OPNET_WGRAD_OVERLAP=1).  The five weight-gradient contractions are independent of each
-                # other and none fills the GPU (pre-pass, 16-64 output tiles, split-K): LSTM2's stay on the main
-                # stream, LSTM1's and dW_pred run beside them (2.61 -> 2.58 ms per step, tools/step_ab.py).  Not the
-                # default: see DESIGN.md section 9 (one unexplained parity failure of the in-line path when it ran
-                # after this one in the same process, found when the round's GPU budget was spent).
+            if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "1") not in ("0", "") and all(need[1:6]):
+                # The five weight-gradient contractions are independent of each other and none fills the GPU (pre-pass,
+                # 16-64 output tiles, split-K): LSTM2's stay on the main stream, LSTM1's and dW_pred run beside them
+                # (2.61 -> 2.58 ms per step, tools/step_ab.py).  OPN_OPNET_WGRAD_OVERLAP=0: all in line.
                 main, side = torch.cuda.current_stream(), _side_stream(dev)
                 ready = torch.cuda.Event()
                 ready.record(main)
@@ -485,11 +523,11 @@ class OPNetTrunkFn(torch.autograd.Function):
                 main.wait_event(done)
                 for t_ in (dw_ih1, dw_hh1, dw_pred):
                     t_.record_stream(main)
-                return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
+                return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2, None
             dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, need[4], need[5])
             dw_pred = _wtt_weight_grad(hs1, dl) if need[3] else None
             dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, x1, hs1, w_ih1, w_hh1, need[1], need[2])
-            return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
+            return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2, None
         dgates2 = _lstm_recurrence_backward(w_hh2, gates2, cells2, dhs2)
         dfb = torch.empty_like(fb)
         sgemm(dgates2, w_ih2, dfb, trans_a=False, trans_b=False, M=B * T, N=6, K=4 * H2, lda=4 * H2, ldb=6, ldc=6)
@@ -524,7 +562,7 @@ class OPNetTrunkFn(torch.autograd.Function):
             dw_ih2, dw_hh2 = _lstm_weight_grads(dgates2, fb, hs2, w_ih2, w_hh2, need[4], need[5])
             dw_pred = _wtt_weight_grad(hs1, dl) if need[3] else None
         dw_ih1, dw_hh1 = _lstm_weight_grads(dgates1, x1, hs1, w_ih1, w_hh1, need[1], need[2])
-        return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2
+        return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2, None
 
 
 class AddLayerNormFn(torch.autograd.Function):
@@ -684,8 +722,14 @@ def linear(x, weight, bias=None, relu: bool = False):
     return LinearFn.apply(x, weight, bias, relu)
 
 
+def _wants_stash(*tensors) -> bool:
+    """True when a backward pass can follow: grad mode on and some input requires grad.  Evaluated by the front-ends
+    because inside autograd.Function.forward grad mode is always off and needs_input_grad ignores torch.no_grad()."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def lstm_layer(x, w_ih, w_hh):
-    return LstmLayerFn.apply(x, w_ih, w_hh)
+    return LstmLayerFn.apply(x, w_ih, w_hh, _wants_stash(x, w_ih, w_hh))
 
 
 def who_to_track(boxes, hs1, w_pred):
@@ -699,7 +743,8 @@ def opnet_fused_available(h1: int, h2: int, pred_dim: int) -> bool:
 
 def opnet_trunk(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2):
     """(hs2 [B,T,H2], who-to-track logits [B,15,T]) of OPNet through the fused forward kernel."""
-    return OPNetTrunkFn.apply(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2)
+    return OPNetTrunkFn.apply(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2,
+                              _wants_stash(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2))
 
 
 def add_layer_norm(x, res, weight, bias, eps: float = 1e-5):

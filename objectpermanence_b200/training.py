@@ -5,7 +5,8 @@ with the model call, the loss and the backward on sm_100a kernels.
     total, pred, cons = step(boxes, labels, mask)    # device tensors or pinned host tensors
 
 The reference's three per-step `.item()` host syncs (training_main.py:212-214) are replaced by
-one 12-byte device->host read of the (total, prediction, consistency) vector.
+one 12-byte device->host read of the (total, prediction, consistency) vector, plus the 16 status bytes of the
+persistent kernels (ops.status_page): a time-out raises OpnError here instead of training on garbage.
 
 `step.pipelined(boxes, labels, mask)` is the asynchronous form ("async logging"): the inputs go to
 the device on a copy stream (double buffered, so the copy of step k+1 overlaps the kernels of step k), the loss
@@ -41,6 +42,8 @@ class TrainingStep:
         self.optimizer = optimizer
         self.device = next(model.parameters()).device
         self._loss_host = torch.empty(3, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else None
+        self._status_host = torch.zeros(4, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+        self._status = ops.status_page(self.device)[:4] if self.device.type == "cuda" else None
         # pipelined form: two slots of (device input buffers, pinned loss vector, completion event)
         self._slots = None
         self._copy_stream = None
@@ -73,7 +76,9 @@ class TrainingStep:
         mask_d = mask.to(dev, non_blocking=True) if mask is not None else None
         loss3 = self.forward_backward(boxes_d, labels_d, mask_d)
         self._loss_host.copy_(loss3, non_blocking=True)
+        self._status_host.copy_(self._status, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        ops.raise_if_failed(self._status_host, self.device, "training step")
         return tuple(float(v) for v in self._loss_host)
 
     # ---- pipelined form -----------------------------------------------------------------------------------
@@ -87,6 +92,7 @@ class TrainingStep:
                     "labels": torch.empty(labels.shape, dtype=labels.dtype, device=self.device),
                     "mask": torch.empty(mask.shape, dtype=mask.dtype, device=self.device) if mask is not None else None,
                     "loss": torch.empty(3, dtype=torch.float32).pin_memory(),
+                    "status": torch.zeros(4, dtype=torch.int32).pin_memory(),
                     "copied": torch.cuda.Event(), "done": torch.cuda.Event(), "free": torch.cuda.Event(),
                 })
         slot = self._slots[self._k & 1]
@@ -110,6 +116,7 @@ class TrainingStep:
         loss3 = self.forward_backward(slot["boxes"], slot["labels"], slot["mask"])
         slot["free"].record(main)
         slot["loss"].copy_(loss3, non_blocking=True)
+        slot["status"].copy_(self._status, non_blocking=True)
         slot["done"].record(main)
         previous = self._pending
         self._pending = slot
@@ -117,6 +124,7 @@ class TrainingStep:
         if previous is None:
             return None
         previous["done"].synchronize()
+        ops.raise_if_failed(previous["status"], self.device, "training step")
         return tuple(float(v) for v in previous["loss"])
 
     def drain(self):
@@ -124,6 +132,6 @@ class TrainingStep:
         if self._pending is None:
             return None
         self._pending["done"].synchronize()
-        out = tuple(float(v) for v in self._pending["loss"])
-        self._pending = None
-        return out
+        pending, self._pending = self._pending, None
+        ops.raise_if_failed(pending["status"], self.device, "training step")
+        return tuple(float(v) for v in pending["loss"])

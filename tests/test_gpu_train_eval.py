@@ -60,9 +60,10 @@ def test_fused_adam_trains_like_torch_adam(cuda_device):
         losses = [s.forward_backward(boxes, labels)[0].item() for s in steps]
         assert abs(losses[0] - losses[1]) <= 1e-5 and abs(losses[0] - losses[2]) <= 1e-5, (it, losses)
     for (k, pa), pb, pc in zip(a.state_dict().items(), b.state_dict().values(), c.state_dict().values()):
-        # Adam divides by sqrt(v): on elements whose gradient is a near-cancelling sum, the summation order of the
-        # split-K atomics (it varies from launch to launch) is amplified; 3.2e-5 was seen once in round 1
-        tol = 5e-5 * max(1.0, pa.abs().max().item())
+        # 2e-5: the one 3.2e-5 outlier of round 1 came from the same root cause as the [11,37] dW_ih2 failure (the fused
+        # backward summing leftover shared memory as the partial products of its first step), not
+        # from the summation order of the split-K atomics
+        tol = 2e-5 * max(1.0, pa.abs().max().item())
         assert (pa - pb).abs().max().item() <= tol and (pa - pc).abs().max().item() <= tol, k
     # the model's state dict still loads into a fresh module (parameters are views of the flat buffer)
     d = ModelsFactory.get_model("opnet", cfg)

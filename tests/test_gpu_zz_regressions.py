@@ -48,7 +48,6 @@ def test_opnet_fused_backward_back_to_back_launches(cuda_device, monkeypatch, T)
             assert err <= 2e-4 * max(1e-3, want.abs().max().item()), (launch, k, err)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: not yet run on a GPU")
 def test_transformer_lstm_train_mode_matches_the_oracle_with_pinned_masks(cuda_device, monkeypatch):
     """Train mode end to end: the (seed, offset) of every dropout site of the run is recorded, the oracle applies the
     restated Philox masks (oracle/dropout_mask.py) at the same sites, and outputs and every gradient must agree."""

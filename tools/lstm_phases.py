@@ -52,3 +52,20 @@ FUSED = ["publish2+stores", "poll h1", "split+barrier", "MMA1+head+barrier", "po
 for cta, off in ((0, 32), (77, 64)):
     ph = words[off:off + 8].tolist()
     print(f"fused fwd cta {cta}: total {sum(ph) / T:7.0f} clk/frame | " + "  ".join(f"{l} {v / T:6.0f}" for l, v in zip(FUSED, ph)), flush=True)
+
+# fused OPNet backward
+probs = torch.softmax(torch.randn(B, T, 15, **f32), -1)
+g1.uniform_(0.05, 0.95); g2.uniform_(0.05, 0.95); c1.normal_(0, 0.5); c2.normal_(0, 0.5)
+dh2 = torch.randn(B, T, H2, **f32) * 0.01
+dg1 = torch.empty(B, T, 4 * H1, **f32); dg2 = torch.empty(B, T, 4 * H2, **f32); dlg = torch.empty(B, T, 15, **f32)
+wsb = torch.zeros(lib.opn_opnet_bwd_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
+for _ in range(2):
+    _lib.check(lib.opn_opnet_bwd(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(), w_ih2.data_ptr(), w_hh2.data_ptr(),
+                                 g1.data_ptr(), c1.data_ptr(), g2.data_ptr(), c2.data_ptr(), dh2.data_ptr(), dg1.data_ptr(), dg2.data_ptr(), dlg.data_ptr(),
+                                 wsb.data_ptr(), wsb.numel(), s))
+torch.cuda.synchronize()
+words = wsb[:4096].view(torch.int64).cpu()
+FUSEDB = ["gather2+reduce", "cell bwd 2", "barrier A", "MMA2+publish+dfb share", "B0+pub+gather dfb", "sum shares (B1,B2)", "head|gather1,B3,cell bwd 1", "MMA1+publish"]
+for cta, off in ((0, 32), (77, 64)):
+    ph = words[off:off + 8].tolist()
+    print(f"fused bwd cta {cta}: total {sum(ph) / T:7.0f} clk/frame | " + "  ".join(f"{l} {v / T:6.0f}" for l, v in zip(FUSEDB, ph)), flush=True)
