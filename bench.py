@@ -13,10 +13,15 @@ Prints ONE JSON line on rank 0 (contract in the task prompt):
   roofline  the dominant kernel of the step (the fused OPNet backward or forward, whichever is longer; its launches
             inside the timed steps are bracketed by CUDA events on the launching stream) against the measured HBM peak;
             `kernels` lists every recurrence kernel with `in_step` marking what the step runs (`ms_alone`: timed alone)
-  cpu_baseline  the oracle port of the reference path on the host cores, bounded sample
-`--impl reference` times only that CPU port (the reference is pure Python on PyTorch and is not
-present on the GPU box; oracle/opnet_oracle.py restates it and calls the same fused CPU LSTM
-the reference's nn.LSTM dispatches to).
+  cpu_baseline  the reference's own CPU implementation on the host cores (the unmodified modules staged in
+            baseline/_ref by oracle/stage_reference.py: kind "reference"; the oracle port only where that copy is
+            absent: kind "port"), bounded sample
+  readings  (N = 1 only) the other BASELINE.json configs and comparators, each timed the same way after the headline
+            region: config 3 (transformer_lstm [32,300], with tensor-pipe utilisation), config 4 (opnet [8,2000], with
+            its HBM fraction), the H2 = 256 reading, the per-GPU batch sweep B = 32 / 128 / 256 ("1 rank x 256"), the
+            1e-2 (bf16-tolerance) arithmetic mode, and the reference nn.Modules on the SAME GPU through PyTorch's
+            cuDNN / cuBLAS path (informational: the kernel to beat on the box; never enters `value`)
+`--impl reference` times the reference's CPU path only (rank 0; other ranks exit 0).
 """
 from __future__ import annotations
 
@@ -42,6 +47,15 @@ FUSED_FWD = os.environ.get("OPN_OPNET_FUSED", "1") not in ("0", "")   # the mode
 FUSED_BWD = FUSED_FWD and os.environ.get("OPN_OPNET_FUSED_BWD", "1") not in ("0", "")   # ... and backward path
 METRIC = "videos/sec OPNet fwd+bwd [B,T=300,N=15,h=256]"
 UNIT = "videos/s"
+WORKLOAD = ("opnet configs/opnet_model_config.json [B=32 per GPU,T=300,N=15,F=6] H1=256 H2=512 fp32, "
+            "zero_grad + fwd + L1 loss + bwd")
+
+
+def config_for(world: int) -> dict:
+    """`config` of the JSON line: ONE definition for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
+            "collective": "one NCCL all-reduce of the flat fp32 gradient per step" if world > 1 else "none",
+            "l2": "256 MB buffer written between timed iterations (untimed)"}
 
 
 def measured_peaks():
@@ -106,17 +120,45 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path
+# CPU arm: the reference's own modules (staged copy) or, where absent, the oracle port
 # ---------------------------------------------------------------------------------------------
+def reference_module(name: str, cfg: dict):
+    """The UNMODIFIED reference nn.Module from baseline/_ref through its own factory, or None when not staged."""
+    from oracle import stage_reference
+    if stage_reference.staged_root() is None:
+        return None
+    stage_reference.import_reference()
+    try:
+        from baselines.models_factory import ModelsFactory as RefFactory   # the reference's public API
+        return RefFactory.get_model(name, dict(cfg))
+    except ImportError:       # the factory also imports the detector / tracker stack; the model classes do not
+        import baselines.learned_models as ref_models
+        return {"opnet": ref_models.OPNet, "transformer_lstm": ref_models.TransformerLstm}[name](dict(cfg))
+
+
 def cpu_reference_steps(steps: int, warmup: int, batch: int):
-    """fwd + L1 loss + bwd of the OPNet restatement on the host cores (all threads)."""
-    from oracle import opnet_oracle as oracle
+    """fwd + L1 loss + bwd of the reference OPNet on the host cores (all threads).  Returns (times, kind)."""
     from objectpermanence_b200.synthetic import make_batch
     torch.set_num_threads(os.cpu_count() or 1)
     boxes_np, labels_np, _ = make_batch(batch, T, FEAT, seed=1234)
     boxes, labels = torch.from_numpy(boxes_np), torch.from_numpy(labels_np)
-    params = {k: v.clone().requires_grad_(True) for k, v in oracle.init_params("opnet", OPNET_CFG, seed=0).items()}
+    torch.manual_seed(0)
+    model = reference_module("opnet", OPNET_CFG)
     times = []
+    if model is not None:
+        model.train()
+        loss_fn = torch.nn.L1Loss(reduction="none")           # baselines/training_main.py:152,192,204
+        for it in range(warmup + steps):
+            model.zero_grad(set_to_none=True)
+            t0 = time.perf_counter()
+            y, _ = model(boxes)
+            torch.mean(loss_fn(y, labels)).backward()
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        return times, "reference"
+    from oracle import opnet_oracle as oracle
+    params = {k: v.clone().requires_grad_(True) for k, v in oracle.init_params("opnet", OPNET_CFG, seed=0).items()}
     for it in range(warmup + steps):
         for v in params.values():
             v.grad = None
@@ -127,7 +169,13 @@ def cpu_reference_steps(steps: int, warmup: int, batch: int):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return times
+    return times, "port"
+
+
+def _cpu_sample_text(steps: int, kind: str) -> str:
+    what = ("unmodified reference modules from baseline/_ref through ModelsFactory.get_model, torch CPU (oneDNN LSTM)"
+            if kind == "reference" else "oracle port, torch fused CPU LSTM (reference copy not staged)")
+    return f"{steps} full steps of the [32,300,15,6] workload ({what})"
 
 
 def run_reference_arm(args):
@@ -135,7 +183,7 @@ def run_reference_arm(args):
     if rank != 0:
         return  # other ranks exit without work
     steps = max(1, args.steps)
-    times = cpu_reference_steps(steps, max(1, min(args.warmup, 2)), B_PER_GPU)
+    times, kind = cpu_reference_steps(steps, max(1, min(args.warmup, 2)), B_PER_GPU)
     sec = sum(times) / len(times)
     value = B_PER_GPU / sec
     cores = os.cpu_count() or 1
@@ -143,10 +191,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "opnet configs/opnet_model_config.json [B=32,T=300,N=15,F=6] H1=256 H2=512, "
-                               "fwd + L1 loss + bwd on CPU"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} full steps of the [32,300,15,6] workload (oracle port, torch fused CPU LSTM)"},
+        "config": config_for(max(1, args.gpus)),   # the GPU arm's config; this arm runs its per-GPU workload on the host cores
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": _cpu_sample_text(steps, kind)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -156,6 +202,141 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+TRANSFORMER_CFG = {"boxes_features_dim": 256, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2,
+                   "lstm_hidden_dim": 512}          # configs/transformer_lstm_model_config.json
+
+
+def _event_time(fn, steps, warmup, flush):
+    """ms per call: CUDA events around each call, an untimed 256 MB L2-flush write between calls."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    pairs = []
+    for i in range(steps):
+        flush.fill_(float(i))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in pairs) / steps
+
+
+def extra_readings(dev, flush, peaks):
+    """The other BASELINE.json configs and comparators (N = 1 only; each reading is independent: a failure is recorded as
+    text and does not touch the headline).  Every figure is zero_grad + forward + L1 loss + backward with device-resident
+    synthetic inputs, timed like the headline."""
+    from objectpermanence_b200.models_factory import ModelsFactory
+    from objectpermanence_b200.synthetic import make_batch
+    from objectpermanence_b200.training import TrainingStep
+    hbm = float(peaks["hbm_gbs"])
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    out = {}
+
+    def ours(name, cfg, B, Tn, feat, steps=5, warmup=3, train=True):
+        torch.manual_seed(0)
+        model = ModelsFactory.get_model(name, cfg).to(dev)
+        model.train(train)
+        step = TrainingStep(model, name)
+        b, l, _ = make_batch(B, Tn, feat, seed=4321)
+        b, l = torch.from_numpy(b).to(dev), torch.from_numpy(l).to(dev)
+        ms = _event_time(lambda: step.forward_backward(b, l), steps, warmup, flush)
+        del step, model, b, l
+        torch.cuda.empty_cache()
+        return ms
+
+    def guarded(key, fn):
+        try:
+            out[key] = fn()
+        except Exception as exc:  # noqa: BLE001 -- a reading must never take the headline down
+            out[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+
+    def config3():
+        ms = ours("transformer_lstm", TRANSFORMER_CFG, 32, 300, 5)
+        attn_flops = 94.4e9 * TRANSFORMER_CFG["num_attention_layers"] * 3     # QK^T + PV, forward + backward (SURVEY 8d)
+        return {"workload": "transformer_lstm configs/transformer_lstm_model_config.json [32,300,15,5] train mode (dropout 0.1)",
+                "ms_per_step": ms, "videos_per_s": 32 / (ms * 1e-3),
+                "tensor_pipe_utilisation": attn_flops / (ms * 1e-3) / (tensor_peak * 1e12),
+                "tensor_pipe_note": f"useful QK^T+PV FLOPs (94.4 GF x 2 layers x 3) / step time / {tensor_peak:.1f} TF sustained bf16 (measured)",
+                "useful_tflops_whole_step": 929e9 / (ms * 1e-3) / 1e12}
+
+    def config4():
+        ms = ours("opnet", OPNET_CFG, 8, 2000, 6)
+        alg = 31700.0 * 8 * 2000 + 17.05e6
+        return {"workload": "opnet [8,2000,15,6] H1=256 H2=512", "ms_per_step": ms, "videos_per_s": 8 / (ms * 1e-3),
+                "algorithmic_bytes": alg, "hbm_frac_whole_step": alg / (ms * 1e-3) / 1e9 / hbm}
+
+    def h2_256():
+        ms = ours("opnet", dict(OPNET_CFG, videos_hidden_dim=256), 32, 300, 6)
+        alg = 21460.0 * 32 * 300 + 3 * 4 * 625920.0
+        return {"workload": "opnet [32,300,15,6] H1=256 H2=256 (videos_hidden_dim=256)", "ms_per_step": ms,
+                "videos_per_s": 32 / (ms * 1e-3), "hbm_frac_whole_step": alg / (ms * 1e-3) / 1e9 / hbm}
+
+    def batch_sweep():
+        res = {}
+        for B in (32, 128, 256):
+            ms = ours("opnet", OPNET_CFG, B, 300, 6, steps=4, warmup=2)
+            alg = 31700.0 * B * 300 + 17.05e6
+            res[f"B{B}"] = {"ms_per_step": ms, "videos_per_s": B / (ms * 1e-3), "hbm_frac_whole_step": alg / (ms * 1e-3) / 1e9 / hbm}
+        res["speedup_B256_over_B32"] = res["B256"]["videos_per_s"] / res["B32"]["videos_per_s"]
+        res["note"] = "opnet [B,300,15,6] on ONE GPU: the '1 rank x 256' strong-scaling reading of SURVEY 8d"
+        return res
+
+    def low_precision():
+        from objectpermanence_b200 import ops
+        if not hasattr(ops, "set_precision"):
+            return {"error": "no reduced-precision mode in this build"}
+        ops.set_precision("bf16")
+        try:
+            ms = ours("opnet", OPNET_CFG, 32, 300, 6)
+        finally:
+            ops.set_precision("fp32")
+        return {"workload": "opnet [32,300,15,6], 1e-2 mode: single-pass 16-bit operands, fp32 accumulation and cell state",
+                "dtype": "bf16", "ms_per_step": ms, "videos_per_s": 32 / (ms * 1e-3)}
+
+    def reference_on_gpu():
+        """The kernel to beat on the same box: the unmodified reference modules on this GPU (cuDNN LSTM, cuBLAS, SDPA)."""
+        res = {}
+        loss_fn = torch.nn.L1Loss(reduction="none")
+        for key, name, cfg, B, feat, steps in (("opnet_32x300", "opnet", OPNET_CFG, 32, 6, 10),
+                                               ("opnet_256x300", "opnet", OPNET_CFG, 256, 6, 4),
+                                               ("transformer_lstm_32x300", "transformer_lstm", TRANSFORMER_CFG, 32, 5, 2)):
+            try:
+                torch.manual_seed(0)
+                model = reference_module(name, cfg)
+                if model is None:
+                    return {"error": "reference not staged (baseline/_ref absent)"}
+                model = model.to(dev).train()
+                b, l, _ = make_batch(B, 300, feat, seed=4321)
+                b, l = torch.from_numpy(b).to(dev), torch.from_numpy(l).to(dev)
+
+                def fn():
+                    model.zero_grad(set_to_none=True)
+                    o = model(b)
+                    y = o[0] if isinstance(o, tuple) else o
+                    torch.mean(loss_fn(y, l)).backward()
+
+                ms = _event_time(fn, steps, 2, flush)
+                res[key] = {"ms_per_step": ms, "videos_per_s": B / (ms * 1e-3)}
+                del model, b, l
+            except Exception as exc:  # noqa: BLE001
+                res[key] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+            torch.cuda.empty_cache()
+        res["note"] = ("unmodified reference nn.Modules from baseline/_ref on this GPU through PyTorch's own kernels "
+                       "(cuDNN LSTM / cuBLAS / SDPA); informational comparator, never part of `value`")
+        return res
+
+    guarded("config3_transformer_lstm", config3)
+    guarded("config4_opnet_8x2000", config4)
+    guarded("opnet_h2_256", h2_256)
+    guarded("batch_sweep_one_gpu", batch_sweep)
+    guarded("precision_1e-2_mode", low_precision)
+    guarded("reference_modules_on_this_gpu", reference_on_gpu)
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from objectpermanence_b200 import _lib, ops
@@ -248,13 +429,24 @@ def run_ours(args):
         e2e_fn = lambda: step(boxes_h, labels_h)
     else:
         e2e_fn = lambda: step.pipelined(boxes_h, labels_h)
-    e2e_ms, _, _, w2 = timed(e2e_fn, args.steps, max(1, args.warmup // 2))
+    e2e_ms, _, w_e0, w2 = timed(e2e_fn, args.steps, max(1, args.warmup // 2))
     step.drain()
+    e2e_wall_s = w2 - w_e0     # host wall clock around the same region (barrier + synchronize on both sides; it also
+                               # contains the 256 MB L2-flush writes between steps, which the event sum leaves out)
     clocks = sampler.stop(w0, w2) if sampler else None
 
     ms_per_step = total_ms / args.steps
     value = world * B_PER_GPU / (ms_per_step * 1e-3)
     e2e_value = world * B_PER_GPU / (e2e_ms / args.steps * 1e-3)
+    e2e_wall_value = world * B_PER_GPU * args.steps / e2e_wall_s
+    grads_identical = None
+    if world > 1:
+        # the averaged flat gradient must be the same bits on every rank (the driver's 1-GPU test box cannot check this)
+        step.forward_backward(boxes_d, labels_d)
+        mx, mn = reducer.flat.clone(), reducer.flat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        grads_identical = bool(torch.equal(mx, mn))
 
     if rank != 0:
         if world > 1:
@@ -385,26 +577,36 @@ def run_ours(args):
                 "whole_step_algorithmic_gbs": (31700.0 * B_PER_GPU * T + 17.05e6) / (ms_per_step * 1e-3) / 1e9}
 
     # CPU baseline: bounded sample of the same workload on the host cores
-    cpu_times = cpu_reference_steps(steps=3, warmup=1, batch=B_PER_GPU)
+    cpu_times, cpu_kind = cpu_reference_steps(steps=3, warmup=1, batch=B_PER_GPU)
     cpu_value = B_PER_GPU / (sum(cpu_times) / len(cpu_times))
+    readings = None
+    if world == 1 and not args.no_readings:
+        del step, model
+        torch.cuda.empty_cache()
+        readings = extra_readings(dev, flush, peaks)
 
     h2d = boxes_h.numel() * 4 + labels_h.numel() * 4
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "opnet configs/opnet_model_config.json [B=32 per GPU,T=300,N=15,F=6] H1=256 H2=512, "
-                               "zero_grad + fwd + L1 loss + bwd" + (" + 1 NCCL grad all-reduce" if world > 1 else ""),
-                   "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
-                   "l2": "256 MB buffer written between timed iterations (untimed)"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+        "config": config_for(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28,
+                "timing": "sum of per-step CUDA-event intervals on the main stream (H2D copies run one step ahead on a copy "
+                          "stream; 12 loss + 16 status bytes read back per step)",
+                "wall_value": e2e_wall_value, "wall_ms_per_step": e2e_wall_s * 1e3 / args.steps,
+                "wall_note": "host wall clock over the same K steps, barrier + synchronize on both sides, L2-flush writes included"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "kernels": kern,
-        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                         "sample": "3 full steps of the [32,300,15,6] workload (oracle port, torch fused CPU LSTM)"},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": cpu_kind,
+                         "sample": _cpu_sample_text(3, cpu_kind)},
     }
+    if grads_identical is not None:
+        line["grads_bit_identical_across_ranks"] = grads_identical
+    if readings is not None:
+        line["readings"] = readings
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -416,6 +618,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-readings", dest="no_readings", action="store_true",
+                    help="skip the extra readings (other configs, comparators) after the headline region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

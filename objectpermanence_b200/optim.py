@@ -74,6 +74,7 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         group = self.param_groups[0]
+        self._check_layout()
         self.steps += 1
         grads = self._gather_grads()
         rc = _lib.load().opn_adam_step(self.numel, self.flat_params.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(),
@@ -83,13 +84,54 @@ class FusedAdam(torch.optim.Optimizer):
         _lib.check(rc, "opn_adam_step")
         return loss
 
-    def state_dict(self):
-        return {"steps": self.steps, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+    def _check_layout(self) -> None:
+        """`model.to(...)` / `.float()` after construction re-allocates the parameters: the flat views would be stale."""
+        base = self.flat_params.data_ptr()
+        for p, o in zip(self._params, self._offsets):
+            if p.data_ptr() != base + 4 * o:
+                raise RuntimeError("FusedAdam: a parameter no longer lives in the flat buffer (the model was moved or cast "
+                                   "after the optimiser was built); construct FusedAdam after model.to(device)")
 
-    def load_state_dict(self, state):
-        self.steps = int(state["steps"])
-        self.exp_avg.copy_(state["exp_avg"])
-        self.exp_avg_sq.copy_(state["exp_avg_sq"])
-        for g, saved in zip(self.param_groups, state["param_groups"]):
-            g.update(saved)
+    def state_dict(self):
+        """The layout of ``torch.optim.Adam.state_dict()``: ``state[i] = {step, exp_avg, exp_avg_sq}`` per parameter (copies
+        of the slices of the flat moment buffers) and ``param_groups[0]["params"] = [0..n)``, so checkpoint helpers and
+        ``torch.optim.Adam.load_state_dict`` accept it and vice versa."""
+        state = {}
+        if self.steps > 0:
+            for i, (p, o) in enumerate(zip(self._params, self._offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.steps)),
+                            "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        groups = []
+        for g in self.param_groups:
+            packed = {k: v for k, v in g.items() if k != "params"}
+            packed["params"] = list(range(len(self._params)))
+            groups.append(packed)
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, state_dict):
+        if "state" not in state_dict or "param_groups" not in state_dict:
+            raise ValueError("FusedAdam.load_state_dict expects the torch.optim layout {'state': ..., 'param_groups': ...}")
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self._params):
+            raise ValueError("FusedAdam.load_state_dict: expected one parameter group with "
+                             f"{len(self._params)} parameters")
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for key, entry in state_dict["state"].items():
+            i = int(key)
+            p, o = self._params[i], self._offsets[i]
+            n = p.numel()
+            if tuple(entry["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"FusedAdam.load_state_dict: moment shape mismatch for parameter {i}")
+            self.exp_avg[o:o + n].copy_(entry["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(entry["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(entry["step"])))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam.load_state_dict: parameters with different step counts are not supported "
+                             "(one bias correction per launch)")
+        self.steps = steps.pop() if steps else 0
+        for g, saved in zip(self.param_groups, groups):
+            g.update({k: v for k, v in saved.items() if k != "params"})

@@ -229,6 +229,44 @@ def test_lstm_inference_mode_skips_stash(cuda_device):
     assert (out.cpu().double() - ref).abs().max().item() <= 2e-5
 
 
+def test_no_grad_skips_the_stash_even_when_the_weights_require_grad(cuda_device, monkeypatch):
+    """needs_input_grad mirrors requires_grad whatever the grad mode: real modules (parameters require grad) under
+    torch.no_grad() must still launch without the gates / cells stash (NULL pointers), LSTM layer and fused OPNet."""
+    seen = {}
+    lib = _lib.load()
+
+    class Spy:
+        def __getattr__(self, name):
+            fn = getattr(lib, name)
+            if name not in ("opn_lstm_fwd", "opn_opnet_fwd"):
+                return fn
+
+            def call(*args):
+                seen[name] = args
+                return fn(*args)
+            return call
+
+    monkeypatch.setattr(ops._lib, "load", lambda: Spy())
+    x, w_ih, w_hh, _ = _lstm_case(4, 9, 6, 128, seed=21)
+    wi, wh = w_ih.to(cuda_device).requires_grad_(True), w_hh.to(cuda_device).requires_grad_(True)
+    with torch.no_grad():
+        out = ops.lstm_layer(x.to(cuda_device), wi, wh)
+    assert seen["opn_lstm_fwd"][6] is None and seen["opn_lstm_fwd"][7] is None     # gates, cells
+    assert not out.requires_grad
+    out = ops.lstm_layer(x.to(cuda_device), wi, wh)
+    assert seen["opn_lstm_fwd"][6] is not None and out.requires_grad
+    H1, H2 = 256, 512
+    w = [(_rand(s_, 70 + i, 0.05)).to(cuda_device).requires_grad_(True) for i, s_ in
+         enumerate([(4 * H1, 90), (4 * H1, H1), (15, H1), (4 * H2, 6), (4 * H2, H2)])]
+    boxes = _rand((2, 5, 15, 6), 9).abs().to(cuda_device)
+    with torch.no_grad():
+        ops.opnet_trunk(boxes, *w)
+    a = seen["opn_opnet_fwd"]
+    assert a[11] is None and a[12] is None and a[17] is None and a[18] is None        # gates1, cells1, gates2, cells2
+    ops.opnet_trunk(boxes, *w)
+    assert seen["opn_opnet_fwd"][11] is not None
+
+
 def test_lstm_unsupported_hidden_size(cuda_device):
     x, w_ih, w_hh, _ = _lstm_case(2, 3, 6, 48, seed=5)
     with pytest.raises(_lib.OpnError, match="unsupported"):

@@ -228,3 +228,75 @@ def test_pipelined_step_returns_lagged_losses(cuda_device):
     assert sb.drain() is None
     for (k, pa), pb in zip(a.state_dict().items(), b.state_dict().values()):
         assert (pa - pb).abs().max().item() <= 1e-6 * max(1.0, pa.abs().max().item()), k
+
+
+# ---- round-2 advisor items -------------------------------------------------------------------------------------
+def test_fused_adam_state_dict_is_interchangeable_with_torch_adam(cuda_device):
+    """state_dict() has torch.optim's layout: a torch.optim.Adam checkpoint resumes in FusedAdam and the other way round."""
+    torch.manual_seed(3)
+    w = [torch.nn.Parameter(torch.randn(7, 5, device=cuda_device)), torch.nn.Parameter(torch.randn(6, device=cuda_device))]
+    v = [torch.nn.Parameter(p.detach().clone()) for p in w]
+    ref, fused = torch.optim.Adam(w, lr=1e-2), FusedAdam(v, lr=1e-2)
+
+    def step(opt, params, seed):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g).to(cuda_device)
+        opt.step()
+
+    for it in range(3):
+        step(ref, w, it), step(fused, v, it)
+    sd = fused.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == [0, 1]
+    assert set(sd["state"][0]) >= {"step", "exp_avg", "exp_avg_sq"} and sd["state"][0]["exp_avg"].shape == (7, 5)
+    # torch's checkpoint -> FusedAdam, FusedAdam's checkpoint -> torch: both continue identically
+    v2 = [torch.nn.Parameter(p.detach().clone()) for p in w]
+    fused2 = FusedAdam(v2, lr=5e-2)
+    fused2.load_state_dict(ref.state_dict())
+    assert fused2.steps == 3 and fused2.param_groups[0]["lr"] == 1e-2
+    w2 = [torch.nn.Parameter(p.detach().clone()) for p in v]
+    ref2 = torch.optim.Adam(w2, lr=5e-2)
+    ref2.load_state_dict(sd)
+    for it in range(3, 5):
+        step(ref, w, it), step(fused2, v2, it), step(ref2, w2, it)
+    for a, b, c in zip(w, v2, w2):
+        assert (a - b).abs().max().item() <= 2e-6 and (a - c).abs().max().item() <= 2e-6
+    with pytest.raises(ValueError, match="torch.optim layout"):
+        fused.load_state_dict({"steps": 1})
+    # moving the parameters after construction invalidates the flat views: loud error instead of a silent no-op
+    v[0].data = v[0].data.clone()
+    v[0].grad = torch.zeros_like(v[0])
+    with pytest.raises(RuntimeError, match="no longer lives in the flat buffer"):
+        fused.step()
+
+
+def test_training_step_raises_when_the_status_page_reports_a_timeout(cuda_device):
+    """The persistent kernels report inter-CTA time-outs into the sticky status page; the training step reads it with the
+    loss.  A non-zero word (planted here from the host) must raise OpnError -- in the blocking and in the pipelined form --
+    and the page is cleared so that the next step runs."""
+    from objectpermanence_b200 import _lib, ops
+    from objectpermanence_b200.training import TrainingStep
+    cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    torch.manual_seed(0)
+    model = ModelsFactory.get_model("opnet", cfg).to(cuda_device)
+    step = TrainingStep(model, "opnet")
+    boxes, labels, _ = make_batch(2, 6, 6, seed=3)
+    boxes, labels = torch.from_numpy(boxes).pin_memory(), torch.from_numpy(labels).pin_memory()
+    good = step(boxes, labels)
+    page = ops.status_page(cuda_device)
+    was_debug = ops._DEBUG_SYNC
+    ops.set_debug_sync(False)       # the per-launch debug check would catch it first
+    try:
+        page[:4] = torch.tensor([1, 7, 3, 5], dtype=torch.int32)
+        with pytest.raises(_lib.OpnError, match="timed out .*step 7, cta 3, thread 5"):
+            step(boxes, labels)
+        assert int(page[0].item()) == 0
+        assert step(boxes, labels) == pytest.approx(good, abs=1e-6)
+        assert step.pipelined(boxes, labels) is None
+        page[:4] = torch.tensor([1, 2, 0, 0], dtype=torch.int32)
+        step.pipelined(boxes, labels)           # returns the (good) loss of the first pipelined step
+        with pytest.raises(_lib.OpnError, match="timed out"):
+            step.drain()
+    finally:
+        page.zero_()
+        ops.set_debug_sync(was_debug)
