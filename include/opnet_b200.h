@@ -94,10 +94,27 @@ OPN_API int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj, co
 OPN_API int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, const float* gates, const float* cells,
                  const float* dh_out, float* dgates, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* 1 when opn_lstm_fwd / opn_lstm_bwd run the batch-wide tcgen05 kernels for this (B, H) (groups of 128 videos, weights in
+ * shared memory, accumulators in TMEM; opn_lstm_tc.cu), 0 for the 8-video mma.sync / FP32-FMA kernels.  The gates / cells
+ * stash of the batch-wide forward has an internal layout: hand it to opn_lstm_bwd of the same (B, H) only. */
+OPN_API int opn_lstm_batchwide(int64_t B, int64_t H);
+
 /* SYNCHRONISES the device.  Reads back the status word the persistent kernels leave in
  * `workspace`: OPN_OK, or OPN_ERR_TIMEOUT if an inter-CTA wait expired (detail words in
  * info[0..2] if info != NULL).  For tests and debugging. */
 OPN_API int opn_lstm_status(const void* workspace, uint32_t* info);
+
+/* ---- arithmetic mode ---------------------------------------------------------------
+ * The tensor-core kernels (recurrences, fused OPNet forward / backward, opn_sgemm's tcgen05 path) multiply 16-bit
+ * operands with fp32 accumulation.  OPN_PRECISION_FP32 (default) carries every fp32 operand as a hi + lo pair and runs
+ * three products per slice (hi.hi + hi.lo + lo.hi, 22 significand bits): predicted boxes within 1e-4 of the reference.
+ * OPN_PRECISION_16BIT runs the hi.hi product alone (one pass, a third of the tensor work; cell state, accumulation and
+ * the stash stay fp32): the north star's "1e-2 bf16" mode -- boxes within 1e-2.  The setting is per calling thread and
+ * applies to the launches enqueued after it. */
+#define OPN_PRECISION_FP32 0
+#define OPN_PRECISION_16BIT 1
+OPN_API int opn_set_precision(int mode);
+OPN_API int opn_get_precision(void);
 
 /* Sticky status page.  `device_page`: >= 4096 zeroed bytes of device memory owned by the caller, registered for the
  * CURRENT device (NULL unregisters).  While one is registered the persistent kernels (opn_lstm_*, opn_opnet_*) report

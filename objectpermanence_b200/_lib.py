@@ -29,8 +29,11 @@ SIGNATURES = {
     "opn_lstm_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "opn_lstm_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "opn_lstm_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "opn_lstm_batchwide": (c_int, [c_int64, c_int64]),
     "opn_lstm_status": (c_int, [_P, POINTER(c_uint32)]),
     "opn_set_status_page": (c_int, [_P]),
+    "opn_set_precision": (c_int, [c_int]),
+    "opn_get_precision": (c_int, []),
     "opn_opnet_fwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "opn_opnet_fwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 16 + [c_int64, _P]),
     "opn_opnet_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),

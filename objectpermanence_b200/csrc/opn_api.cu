@@ -29,6 +29,10 @@ unsigned int* status_page_or(void* workspace_head) {
     return static_cast<unsigned int*>(workspace_head);
 }
 
+// arithmetic mode of the recurrence / contraction kernels (opn_set_precision)
+static thread_local int g_precision = OPN_PRECISION_FP32;
+int current_precision() { return g_precision; }
+
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return OPN_ERR_CUDA;
@@ -41,6 +45,14 @@ extern "C" int opn_version(void) { return 100; /* 0.1.0 */ }
 extern "C" const char* opn_last_error(void) { return opn::g_error; }
 
 extern "C" unsigned long long opn_launch_count(void) { return opn::g_launch_count; }
+
+extern "C" int opn_set_precision(int mode) {
+    OPN_CHECK_ARG(mode == OPN_PRECISION_FP32 || mode == OPN_PRECISION_16BIT, "set_precision: unknown mode %d", mode);
+    opn::g_precision = mode;
+    return OPN_OK;
+}
+
+extern "C" int opn_get_precision(void) { return opn::g_precision; }
 
 extern "C" int opn_set_status_page(void* device_page) {
     int dev = 0;

@@ -561,6 +561,11 @@ int run_bwd(const BwdParams& p, int64_t B, cudaStream_t s, bool cluster_ok) {
 }  // namespace opn
 
 namespace opn {
+// batch-wide tcgen05 flavour (opn_lstm_tc.cu): groups of 128 videos, weights in shared memory, accumulators in TMEM
+bool lstm_tc_wanted(int64_t B, int64_t H);
+size_t lstm_tc_workspace_bytes(int64_t B, int64_t H);
+int lstm_fwd_tc(const FwdParams& p, int64_t B, int64_t H, void* workspace, cudaStream_t s);
+int lstm_bwd_tc(const BwdParams& p, int64_t B, int64_t H, void* workspace, cudaStream_t s);
 // tensor-core flavour of the recurrence (opn_lstm_mma.cu)
 bool lstm_mma_supported(int64_t H);
 int lstm_fwd_mma(const FwdParams& p, int64_t B, int64_t H, cudaStream_t s);
@@ -579,7 +584,8 @@ static bool want_mma(int64_t H) {
 
 extern "C" int64_t opn_lstm_workspace_bytes(int64_t B, int64_t T, int64_t H) {
     if (B <= 0 || T <= 0 || H <= 0) return 0;
-    return (int64_t)layout(B, T, H).total;
+    const size_t ring = layout(B, T, H).total, tcb = lstm_tc_workspace_bytes(B, H);
+    return (int64_t)(ring > tcb ? ring : tcb);
 }
 
 extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj, const float* w_hh, float* hs,
@@ -592,10 +598,18 @@ extern "C" int opn_lstm_fwd(int64_t B, int64_t T, int64_t H, const float* xproj,
     OPN_CHECK_ARG(xproj && w_hh && hs && workspace, "lstm_fwd: null pointer");
     OPN_CHECK_ARG((gates == nullptr) == (cells == nullptr), "lstm_fwd: gates and cells must both be given or both NULL");
     const WorkspaceLayout l = layout(B, T, H);
-    OPN_CHECK_ARG(workspace_bytes >= (int64_t)l.total, "lstm_fwd: workspace too small (%lld < %lld)",
-                  (long long)workspace_bytes, (long long)l.total);
+    OPN_CHECK_ARG(workspace_bytes >= opn_lstm_workspace_bytes(B, T, H), "lstm_fwd: workspace too small (%lld < %lld)",
+                  (long long)workspace_bytes, (long long)opn_lstm_workspace_bytes(B, T, H));
     cudaStream_t s = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
+    if (lstm_tc_wanted(B, H)) {
+        FwdParams q;
+        q.xproj = xproj, q.w_hh = w_hh, q.hs = hs, q.gates = gates, q.cells = cells;
+        q.ring = nullptr;
+        q.status = status_page_or(ws);
+        q.B = (int)B, q.T = (int)T, q.group_offset = 0, q.n_slices = 0;
+        return lstm_fwd_tc(q, B, H, ws, s);
+    }
     OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, l.bwd_ring_off - l.status_off, s));  // status + forward ring
     FwdParams p;
     p.xproj = xproj;
@@ -630,9 +644,17 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
     }
     OPN_CHECK_ARG(w_hh && gates && cells && dh_out && dgates && workspace, "lstm_bwd: null pointer");
     const WorkspaceLayout l = layout(B, T, H);
-    OPN_CHECK_ARG(workspace_bytes >= (int64_t)l.total, "lstm_bwd: workspace too small");
+    OPN_CHECK_ARG(workspace_bytes >= opn_lstm_workspace_bytes(B, T, H), "lstm_bwd: workspace too small");
     cudaStream_t s = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
+    if (lstm_tc_wanted(B, H)) {
+        BwdParams q;
+        q.w_hh = w_hh, q.gates = gates, q.cells = cells, q.dh_out = dh_out, q.dgates = dgates;
+        q.ring = nullptr;
+        q.status = status_page_or(ws);
+        q.B = (int)B, q.T = (int)T, q.group_offset = 0, q.n_slices = 0;
+        return lstm_bwd_tc(q, B, H, ws, s);
+    }
     OPN_CUDA(cudaMemsetAsync(ws + l.status_off, 0, 4096, s));
     OPN_CUDA(cudaMemsetAsync(ws + l.bwd_ring_off, 0, l.total - l.bwd_ring_off, s));
     BwdParams p;
@@ -656,6 +678,8 @@ extern "C" int opn_lstm_bwd(int64_t B, int64_t T, int64_t H, const float* w_hh, 
         default: return run_bwd<16, 2>(p, B, s, false);
     }
 }
+
+extern "C" int opn_lstm_batchwide(int64_t B, int64_t H) { return lstm_tc_wanted(B, H) ? 1 : 0; }
 
 extern "C" int opn_lstm_status(const void* workspace, uint32_t* info) {
     OPN_CHECK_ARG(workspace != nullptr, "lstm_status: null workspace");

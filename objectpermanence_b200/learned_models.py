@@ -97,7 +97,7 @@ class OPNet(AbstractCaterModel, _WhoToTrackMixin):
     def forward(self, boxes: torch.Tensor):
         self._check(boxes)
         l1, l2, wp = self.object_to_track_LSTM, self.video_LSTM, self.object_to_track_prediction.weight
-        if ops.opnet_fused_available(l1.hidden_size, l2.hidden_size, wp.shape[0]):
+        if ops.opnet_fused_available(l1.hidden_size, l2.hidden_size, wp.shape[0], boxes.shape[0]):
             # one persistent kernel for LSTM1 + who-to-track + LSTM2 (shipped config)
             h2, logits = ops.opnet_trunk(boxes, l1.weight_ih_l0, l1.weight_hh_l0, wp, l2.weight_ih_l0, l2.weight_hh_l0)
             return self.prediction_layer(h2), logits

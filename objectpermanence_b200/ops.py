@@ -736,9 +736,13 @@ def who_to_track(boxes, hs1, w_pred):
     return WhoToTrackFn.apply(boxes, hs1, w_pred)
 
 
-def opnet_fused_available(h1: int, h2: int, pred_dim: int) -> bool:
-    """The fused OPNet forward exists for the shipped config; OPN_OPNET_FUSED=0 selects the separate kernels."""
-    return (h1, h2, pred_dim) == (256, 512, 15) and os.environ.get("OPN_OPNET_FUSED", "1") not in ("0", "")
+def opnet_fused_available(h1: int, h2: int, pred_dim: int, batch: int = 0) -> bool:
+    """The fused OPNet forward exists for the shipped config; OPN_OPNET_FUSED=0 selects the separate kernels.  At per-GPU
+    batches where the batch-wide tcgen05 recurrence takes LSTM2 (opn_lstm_batchwide: groups of 128 videos instead of
+    sequential waves of 32) the separate kernels are the faster path and are used."""
+    if (h1, h2, pred_dim) != (256, 512, 15) or os.environ.get("OPN_OPNET_FUSED", "1") in ("0", ""):
+        return False
+    return not (batch > 0 and _lib.load().opn_lstm_batchwide(batch, h2))
 
 
 def opnet_trunk(boxes, w_ih1, w_hh1, w_pred, w_ih2, w_hh2):

@@ -1,5 +1,6 @@
-"""The reference arm of bench.py (the CPU restatement of the reference path, timed on the host cores) must keep
-printing the JSON line the driver parses -- it is the one place outside tests/ and smoke() that may execute oracle/."""
+"""The reference arm of bench.py (the reference's own CPU path timed on the host cores: the unmodified modules staged in
+baseline/_ref, or the oracle port where that copy is absent) must keep printing the JSON line the driver parses -- it is the
+one place outside tests/ and smoke() that may execute oracle/."""
 import json
 import os
 import subprocess
@@ -15,9 +16,13 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "videos/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    staged = os.path.exists(os.path.join(REPO, "baseline", "_ref", "baselines", "learned_models.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+    sys.path.insert(0, REPO)
+    import bench
+    assert line["config"] == bench.config_for(1)      # the same config dictionary as the GPU arm prints
 
 
 def test_reference_arm_other_ranks_exit_without_work():

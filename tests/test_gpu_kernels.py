@@ -221,6 +221,45 @@ def test_lstm_long_sequence_all_flavours(cuda_device, monkeypatch, flavour, H, T
         assert err <= 1e-4 * scale, (name, err, scale)
 
 
+# ---- batch-wide tcgen05 recurrence (opn_lstm_tc.cu): groups of 128 videos, weights in shared memory, TMEM accumulators ----
+@pytest.mark.parametrize("H", [256, 512])
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (40, 9), (128, 6), (130, 17), (256, 5)])
+def test_lstm_tcgen05_forward_backward(cuda_device, monkeypatch, H, B, T):
+    """OPN_LSTM_TC=1 forces the batch-wide kernels at every batch size: ragged groups (B % 128 != 0), two groups, T = 1."""
+    monkeypatch.setenv("OPN_LSTM_TC", "1")
+    x, w_ih, w_hh, dh = _lstm_case(B, T, 6, H, seed=7 * H + B + T)
+    xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
+    ref = oracle.lstm_layer(xr, wir, whr)
+    ref.backward(dh.double())
+    xg, wig, whg = [t.to(cuda_device).requires_grad_(True) for t in (x, w_ih, w_hh)]
+    out = ops.lstm_layer(xg, wig, whg)
+    out.backward(dh.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5
+    for name, got, want in (("dx", xg.grad, xr.grad), ("dw_ih", wig.grad, wir.grad), ("dw_hh", whg.grad, whr.grad)):
+        scale = max(1.0, want.abs().max().item())
+        err = (got.cpu().double() - want).abs().max().item()
+        assert err <= 5e-5 * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("H", [256, 512])
+def test_lstm_tcgen05_long_sequence_and_saturating_weights(cuda_device, monkeypatch, H):
+    """T = 300 (299 exchanges, every ring slot reused ~150 times) at default-init weights, and x8 weights at T = 40."""
+    monkeypatch.setenv("OPN_LSTM_TC", "1")
+    for B, T, scale, tol_h, tol_g in ((140, 300, 1.0, 2e-5, 1e-4), (9, 40, 8.0, 1e-4, 1e-3)):
+        x, w_ih, w_hh, dh = _lstm_case(B, T, 90, H, seed=31, scale=scale)
+        dh = dh * 0.01
+        xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
+        ref = oracle.lstm_layer(xr, wir, whr)
+        ref.backward(dh.double())
+        xg, wig, whg = [t.to(cuda_device).requires_grad_(True) for t in (x, w_ih, w_hh)]
+        out = ops.lstm_layer(xg, wig, whg)
+        out.backward(dh.to(cuda_device))
+        assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= tol_h
+        for name, got, want in (("dx", xg.grad, xr.grad), ("dw_ih", wig.grad, wir.grad), ("dw_hh", whg.grad, whr.grad)):
+            err = (got.cpu().double() - want).abs().max().item()
+            assert err <= tol_g * max(1.0, want.abs().max().item()), (name, err)
+
+
 def test_lstm_inference_mode_skips_stash(cuda_device):
     x, w_ih, w_hh, _ = _lstm_case(4, 9, 6, 128, seed=21)
     ref = oracle.lstm_layer(x.double(), w_ih.double(), w_hh.double())

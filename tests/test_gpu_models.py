@@ -102,6 +102,18 @@ def test_opnet_long_sequence_config_4(cuda_device):
     _oracle_vs_module("opnet", OPNET_CFG, 8, 2000, cuda_device, seed=2, grad_tol=5e-4)
 
 
+@pytest.mark.parametrize("B,T", [(256, 48), (200, 300)])
+def test_opnet_large_per_gpu_batch_takes_the_batch_wide_tcgen05_recurrence(cuda_device, B, T):
+    """Per-GPU batches of 192 videos and more: LSTM2 runs on the batch-wide tcgen05 kernels (groups of 128 videos, the
+    second one ragged at B = 200), the model around them on the separate kernels -- same 1e-4 bar against the fp64 oracle
+    (the "1 rank x 256" reading of BASELINE config 5)."""
+    from objectpermanence_b200 import _lib
+    assert _lib.load().opn_lstm_batchwide(B, 512) == 1 and _lib.load().opn_lstm_batchwide(32, 512) == 0
+    assert not ops.opnet_fused_available(256, 512, 15, B) and ops.opnet_fused_available(256, 512, 15, 32)
+    y, y_ref, labels = _oracle_vs_module("opnet", OPNET_CFG, B, T, cuda_device, seed=5)
+    assert round(oracle.mean_iou(y, labels), 3) == round(oracle.mean_iou(y_ref.astype(np.float32), labels), 3)
+
+
 def test_opnet_no_labels_loss(cuda_device):
     _oracle_vs_module("opnet_no_labels", OPNET_CFG, 5, 64, cuda_device, seed=4)
 

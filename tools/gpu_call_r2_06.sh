@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -k "tcgen05" > gpurun_out/r02_06_tc_tests.log 2>&1; tail -4 gpurun_out/r02_06_tc_tests.log
+TC_BATCHES=128,256,512 timeout 600 python tools/lstm_tc_time.py > gpurun_out/r02_06_tc_time.log 2>&1; grep tcgen05 gpurun_out/r02_06_tc_time.log
