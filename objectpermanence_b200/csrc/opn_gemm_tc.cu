@@ -28,6 +28,7 @@
 #include "opn_common.cuh"
 
 namespace opn {
+int current_precision();   // opn_api.cu
 namespace {
 
 constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3;
@@ -157,6 +158,7 @@ struct TcParams {
     int kb_per_split;
     float alpha;
     int beta_one, relu, atomic_out;
+    int single;            // 1e-2 arithmetic mode: the hi.hi product alone (lo tiles neither loaded nor multiplied)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -216,12 +218,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 const int kb0 = split * p.kb_per_split, kb1 = min(p.nkb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait_spin(&empty_bar[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[stage], p.single ? 2 * TILE_BYTES : STAGE_BYTES);
                     const uint32_t sbase = ring + stage * STAGE_BYTES;
                     tma_load_2d(sbase + 0 * TILE_BYTES, &map_ahi, kb * TBK, tm * TBM, &full_bar[stage]);
-                    tma_load_2d(sbase + 1 * TILE_BYTES, &map_alo, kb * TBK, tm * TBM, &full_bar[stage]);
                     tma_load_2d(sbase + 2 * TILE_BYTES, &map_bhi, kb * TBK, tn * TBN, &full_bar[stage]);
-                    tma_load_2d(sbase + 3 * TILE_BYTES, &map_blo, kb * TBK, tn * TBN, &full_bar[stage]);
+                    if (!p.single) {
+                        tma_load_2d(sbase + 1 * TILE_BYTES, &map_alo, kb * TBK, tm * TBM, &full_bar[stage]);
+                        tma_load_2d(sbase + 3 * TILE_BYTES, &map_blo, kb * TBK, tn * TBN, &full_bar[stage]);
+                    }
                     if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -248,8 +252,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         const uint64_t bh = make_smem_desc_sw128(sbase + 2 * TILE_BYTES + k16 * 32);
                         const uint64_t bl = make_smem_desc_sw128(sbase + 3 * TILE_BYTES + k16 * 32);
                         umma_bf16(tmem_acc, ah, bh, (kb > kb0 || k16 > 0) ? 1u : 0u);
-                        umma_bf16(tmem_acc, ah, bl, 1u);
-                        umma_bf16(tmem_acc, al, bh, 1u);
+                        if (!p.single) {
+                            umma_bf16(tmem_acc, ah, bl, 1u);
+                            umma_bf16(tmem_acc, al, bh, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);                  // stage may be refilled when these retire
                     if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
@@ -462,6 +468,7 @@ int gemm_tc(int trans_a, int trans_b, long long M, long long N, long long K, flo
     p.beta_one = beta == 1.0f;
     p.relu = relu;
     p.atomic_out = splits > 1;
+    p.single = current_precision() == OPN_PRECISION_16BIT ? 1 : 0;
     if (splits > 1 && !p.beta_one) {
         const long long n = M * N;
         zero_strided_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(C, ldc, (int)M, (int)N);

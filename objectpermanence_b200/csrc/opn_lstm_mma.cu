@@ -37,7 +37,8 @@ namespace {
 // of 16 rows; the KS = H/16 k-steps are split in two halves, warp = (m-tile, K half).  Per step:
 //   gather (poll flagged fp32 fragments, split to fp16, STS.128)  | barrier |  KS/2 x 3 MMAs per warp, partial
 //   pre-activations to shared memory  | barrier |  pointwise (two lanes per cell), publish h_t.
-template <int H, int RG>
+// SINGLE: the 1e-2 arithmetic mode (opn_set_precision): the hi.hi product alone, a third of the MMAs
+template <int H, int RG, bool SINGLE>
 __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const FwdParams p) {
     constexpr int NT = kThreads * RG;
     constexpr int NW = 4 * RG;
@@ -172,8 +173,10 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
                     mma_f16(dm1, ahi[j], b.x, b.y);
                 else
                     mma_f16(dm0, ahi[j], b.x, b.y);
-                mma_f16(ds0, ahi[j], b.z, b.w);
-                mma_f16(ds1, alo[j], b.x, b.y);
+                if constexpr (!SINGLE) {
+                    mma_f16(ds0, ahi[j], b.z, b.w);
+                    mma_f16(ds1, alo[j], b.x, b.y);
+                }
             }
             // D fragment: (row g, videos 2tq, 2tq+1), (row g+8, same videos)
             const float2 lo2 = make_float2(((dm0[0] + dm1[0]) + (ds0[0] + ds1[0])) * winv,
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_fwd_mma_kernel(const Fwd
 // partial[k][b] = sum_{own rows lr} W_hh[row(lr)][k] * da[b][lr]:  M = H columns (H/16 m-tiles, H/(64*RG) per
 // warp), N = 8 videos, K = R = 4U own gate rows (2*RG k-steps).  The B operand is da of the CTA's own cells, scaled
 // per video to [2^10, 2^11) and split to fp16 by the lanes that compute it.
-template <int H, int RG>
+template <int H, int RG, bool SINGLE>
 __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const BwdParams p) {
     constexpr int NT = kThreads * RG;
     constexpr int NW = 4 * RG;
@@ -447,8 +450,10 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
 #pragma unroll
                 for (int ks = 0; ks < KSB; ++ks) {
                     mma_f16(dm, ahi[mi][ks], bf[ks].x, bf[ks].y);
-                    mma_f16(ds, ahi[mi][ks], bf[ks].z, bf[ks].w);
-                    mma_f16(ds, alo[mi][ks], bf[ks].x, bf[ks].y);
+                    if constexpr (!SINGLE) {
+                        mma_f16(ds, ahi[mi][ks], bf[ks].z, bf[ks].w);
+                        mma_f16(ds, alo[mi][ks], bf[ks].x, bf[ks].y);
+                    }
                 }
                 // D: (column kc, videos 2tq, 2tq+1), (column kc+8, same videos), kc = (warp*MPW + mi)*16 + g;
                 // column k belongs to consumer k / U, unit k % U: word [consumer][b][producer = slice][unit].
@@ -517,24 +522,32 @@ __global__ void __launch_bounds__(kThreads* RG, 1) lstm_bwd_mma_kernel(const Bwd
 // ---- dispatch (called from opn_lstm.cu) ----------------------------------------------------------------
 bool lstm_mma_supported(int64_t H) { return H == 256 || H == 512; }
 
+int current_precision();   // opn_api.cu
+
 int lstm_fwd_mma(const FwdParams& p, int64_t B, int64_t H, cudaStream_t s) {
+    const bool single = current_precision() == OPN_PRECISION_16BIT;
     if (H == 256) {
         const char* e = getenv("OPN_LSTM_FWD256_RG");
-        if (e && e[0] == '2') return launch_ring(lstm_fwd_mma_kernel<256, 2>, p, 2 * kThreads, 16, 0, B, s, "lstm_fwd");
-        return launch_ring(lstm_fwd_mma_kernel<256, 1>, p, kThreads, 32, 0, B, s, "lstm_fwd");
+        if (e && e[0] == '2') return launch_ring(lstm_fwd_mma_kernel<256, 2, false>, p, 2 * kThreads, 16, 0, B, s, "lstm_fwd");
+        if (single) return launch_ring(lstm_fwd_mma_kernel<256, 1, true>, p, kThreads, 32, 0, B, s, "lstm_fwd");
+        return launch_ring(lstm_fwd_mma_kernel<256, 1, false>, p, kThreads, 32, 0, B, s, "lstm_fwd");
     }
-    return launch_ring(lstm_fwd_mma_kernel<512, 2>, p, 2 * kThreads, 32, 0, B, s, "lstm_fwd");
+    if (single) return launch_ring(lstm_fwd_mma_kernel<512, 2, true>, p, 2 * kThreads, 32, 0, B, s, "lstm_fwd");
+    return launch_ring(lstm_fwd_mma_kernel<512, 2, false>, p, 2 * kThreads, 32, 0, B, s, "lstm_fwd");
 }
 
 int lstm_bwd_mma(const BwdParams& p, int64_t B, int64_t H, cudaStream_t s) {
+    const bool single = current_precision() == OPN_PRECISION_16BIT;
     if (H == 256) {
         // 16-unit CTAs: 16 producers per batch group instead of 32 halve the reduce-scatter traffic (every producer sends
         // a partial [8, H] whatever its size): 1.92 against 2.31 us/step.  OPN_LSTM_BWD256_RG=1 selects 8-unit CTAs.
         const char* e = getenv("OPN_LSTM_BWD256_RG");
-        if (e && e[0] == '1') return launch_ring(lstm_bwd_mma_kernel<256, 1>, p, kThreads, 32, 0, B, s, "lstm_bwd");
-        return launch_ring(lstm_bwd_mma_kernel<256, 2>, p, 2 * kThreads, 16, 0, B, s, "lstm_bwd");
+        if (e && e[0] == '1') return launch_ring(lstm_bwd_mma_kernel<256, 1, false>, p, kThreads, 32, 0, B, s, "lstm_bwd");
+        if (single) return launch_ring(lstm_bwd_mma_kernel<256, 2, true>, p, 2 * kThreads, 16, 0, B, s, "lstm_bwd");
+        return launch_ring(lstm_bwd_mma_kernel<256, 2, false>, p, 2 * kThreads, 16, 0, B, s, "lstm_bwd");
     }
-    return launch_ring(lstm_bwd_mma_kernel<512, 2>, p, 2 * kThreads, 32, 0, B, s, "lstm_bwd");
+    if (single) return launch_ring(lstm_bwd_mma_kernel<512, 2, true>, p, 2 * kThreads, 32, 0, B, s, "lstm_bwd");
+    return launch_ring(lstm_bwd_mma_kernel<512, 2, false>, p, 2 * kThreads, 32, 0, B, s, "lstm_bwd");
 }
 
 }  // namespace opn

@@ -198,6 +198,8 @@ __device__ __forceinline__ int tma_gather(SweepState& st, uint64_t* bars, unsign
     }
 }
 
+// SINGLE: the 1e-2 arithmetic mode (opn_set_precision): the hi.hi product alone, a third of the MMAs
+template <bool SINGLE>
 __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint4* bfrag2_s = reinterpret_cast<uint4*>(smem + OFF_BFRAG2);
@@ -401,8 +403,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
                     const uint4 ah = a1_s[((mt1 * KS1 + ks) * 2 + 0) * 32 + lane];
                     const uint4 al = a1_s[((mt1 * KS1 + ks) * 2 + 1) * 32 + lane];
                     mma_f16(dm, ah, b.x, b.y);
-                    mma_f16(ds, ah, b.z, b.w);
-                    mma_f16(ds, al, b.x, b.y);
+                    if constexpr (!SINGLE) {
+                        mma_f16(ds, ah, b.z, b.w);
+                        mma_f16(ds, al, b.x, b.y);
+                    }
                 }
                 float* d = d1_s + (kq * 32 + mt1 * 16 + g) * 8 + 2 * tq;
                 *reinterpret_cast<float2*>(d) = make_float2((dm[0] + ds[0]) * winv1, (dm[1] + ds[1]) * winv1);
@@ -417,8 +421,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
                     const uint4 ah = ap_s[(ks * 2 + 0) * 32 + lane];
                     const uint4 al = ap_s[(ks * 2 + 1) * 32 + lane];
                     mma_f16(dm, ah, b.x, b.y);
-                    mma_f16(ds, ah, b.z, b.w);
-                    mma_f16(ds, al, b.x, b.y);
+                    if constexpr (!SINGLE) {
+                        mma_f16(ds, ah, b.z, b.w);
+                        mma_f16(ds, al, b.x, b.y);
+                    }
                 }
                 float* d = dl_s + (warp * 16 + g) * 8 + 2 * tq;
                 *reinterpret_cast<float2*>(d) = make_float2((dm[0] + ds[0]) * winvp, (dm[1] + ds[1]) * winvp);
@@ -540,8 +546,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
                     opn::mma_f16(dm1, ahi[j], b.x, b.y);
                 else
                     opn::mma_f16(dm0, ahi[j], b.x, b.y);
-                opn::mma_f16(ds0, ahi[j], b.z, b.w);
-                opn::mma_f16(ds1, alo[j], b.x, b.y);
+                if constexpr (!SINGLE) {
+                    opn::mma_f16(ds0, ahi[j], b.z, b.w);
+                    opn::mma_f16(ds1, alo[j], b.x, b.y);
+                }
             }
             float* d = d2_s + (kp2 * 64 + lr2_a) * 8 + 2 * tq;
             *reinterpret_cast<float2*>(d) = make_float2(((dm0[0] + dm1[0]) + (ds0[0] + ds1[0])) * winv2,
@@ -629,6 +637,7 @@ FusedLayout fused_layout(int64_t B) {
 }  // namespace
 }  // namespace opn
 
+namespace opn { int current_precision(); }
 using namespace opn;
 
 extern "C" int64_t opn_opnet_fwd_workspace_bytes(int64_t B, int64_t T) {
@@ -682,5 +691,7 @@ extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 32;
-    return launch_ring(opnet_fwd_fused_kernel, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
+    if (current_precision() == OPN_PRECISION_16BIT)
+        return launch_ring(opnet_fwd_fused_kernel<true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
+    return launch_ring(opnet_fwd_fused_kernel<false>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
 }

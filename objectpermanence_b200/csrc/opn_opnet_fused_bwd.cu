@@ -111,6 +111,8 @@ __device__ __forceinline__ bool take_sweep(uint4 (&v)[NV], const uint4* land, Ad
 // parity of ring slots that are reused every 4 steps
 __device__ __forceinline__ uint32_t step_parity4(int s) { return ((uint32_t)(s >> 2) & 1u) ^ 1u; }
 
+// SINGLE: the 1e-2 arithmetic mode (opn_set_precision): the hi.hi product alone, a third of the MMAs
+template <bool SINGLE>
 __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint4* a1_s = reinterpret_cast<uint4*>(smem + OFF_A1);
@@ -385,8 +387,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
 #pragma unroll
                     for (int ks = 0; ks < KSB2; ++ks) {   // three independent accumulation chains of KSB2 MMAs
                         opn::mma_f16(dm, ahi[mi][ks], bf[ks].x, bf[ks].y);
-                        opn::mma_f16(ds, ahi[mi][ks], bf[ks].z, bf[ks].w);
-                        opn::mma_f16(dt, alo[mi][ks], bf[ks].x, bf[ks].y);
+                        if constexpr (!SINGLE) {
+                            opn::mma_f16(ds, ahi[mi][ks], bf[ks].z, bf[ks].w);
+                            opn::mma_f16(dt, alo[mi][ks], bf[ks].x, bf[ks].y);
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) ds[q] += dt[q];
@@ -405,8 +409,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
                 const uint4 ah = ax_s[warp * 64 + lane], al = ax_s[warp * 64 + 32 + lane];
                 const uint4 bw = bfp[warp * 32 + lane];
                 mma_f16(dm, ah, bw.x, bw.y);
-                mma_f16(ds, ah, bw.z, bw.w);
-                mma_f16(ds, al, bw.x, bw.y);
+                if constexpr (!SINGLE) {
+                    mma_f16(ds, ah, bw.z, bw.w);
+                    mma_f16(ds, al, bw.x, bw.y);
+                }
                 // D: (feature g, videos 2tq, 2tq+1); rows g >= 8 are padding
                 *reinterpret_cast<float2*>(dfbp_s + (warp * 8 + g) * 8 + 2 * tq) = make_float2(dm[0] + ds[0], dm[1] + ds[1]);
             }
@@ -584,8 +590,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
                 for (int ks = 0; ks < KSB1; ++ks) {
                     const uint4 ah = a1_s[(mt * KSB1 + ks) * 64 + lane], al = a1_s[(mt * KSB1 + ks) * 64 + 32 + lane];
                     mma_f16(dm, ah, bf[ks].x, bf[ks].y);
-                    mma_f16(ds, ah, bf[ks].z, bf[ks].w);
-                    mma_f16(ds, al, bf[ks].x, bf[ks].y);
+                    if constexpr (!SINGLE) {
+                        mma_f16(ds, ah, bf[ks].z, bf[ks].w);
+                        mma_f16(ds, al, bf[ks].x, bf[ks].y);
+                    }
                 }
                 // column k = mt*16 + g + 8*(q>>1): consumers 2*mt + (q>>1) (8 units each), unit g
                 uint32_t* base = pub1 + mi * (2 * kGroup * NS * U1);
@@ -621,6 +629,7 @@ FusedBwdLayout fused_bwd_layout(int64_t B) {
 }  // namespace
 }  // namespace opn
 
+namespace opn { int current_precision(); }
 using namespace opn;
 
 extern "C" int64_t opn_opnet_bwd_workspace_bytes(int64_t B, int64_t T) {
@@ -661,5 +670,7 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.status = status_page_or(ws + l.status_off);
     p.B = (int)B, p.T = (int)T;
     p.group_offset = 0, p.n_slices = NS;
-    return launch_ring(opnet_bwd_fused_kernel, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+    if (current_precision() == OPN_PRECISION_16BIT)
+        return launch_ring(opnet_bwd_fused_kernel<true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+    return launch_ring(opnet_bwd_fused_kernel<false>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
 }

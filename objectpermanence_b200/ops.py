@@ -23,6 +23,23 @@ def set_debug_sync(flag: bool) -> None:
     _DEBUG_SYNC = bool(flag)
 
 
+PRECISIONS = {"fp32": 0, "bf16": 1, "16bit": 1}
+
+
+def set_precision(mode: str) -> None:
+    """Arithmetic mode of the tensor-core kernels (C ABI: opn_set_precision).  "fp32" (default): every fp32 operand is a
+    hi + lo pair of 16-bit numbers, three products per slice, predicted boxes within 1e-4 of the reference.  "bf16" (alias
+    "16bit"): the north star's 1e-2 mode -- one 16-bit pass with fp32 accumulation, fp32 cell state and stash; a third of
+    the tensor work.  Applies to the kernels launched afterwards by this thread."""
+    if mode not in PRECISIONS:
+        raise ValueError(f"unknown precision {mode!r} (known: {sorted(PRECISIONS)})")
+    _lib.check(_lib.load().opn_set_precision(PRECISIONS[mode]), "opn_set_precision")
+
+
+def get_precision() -> str:
+    return "bf16" if _lib.load().opn_get_precision() == 1 else "fp32"
+
+
 class LaunchTimer:
     """Optional CUDA-event brackets around the two persistent OPNet launches, on the stream they are launched on.
     bench.py installs one for its timed region so that the roofline figure of the dominant kernel comes from the
