@@ -565,7 +565,7 @@ def run_ours(args):
     dom = max(in_step, key=lambda k: kern[k]["ms"])
     hbm_peak = float(peaks["hbm_gbs"])
     traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-    tpath = os.path.join(REPO, "profiles", "r01_kernel_traffic.json")
+    tpath = os.path.join(REPO, "profiles", "r02_kernel_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(dom)

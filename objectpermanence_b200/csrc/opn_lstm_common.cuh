@@ -241,11 +241,25 @@ int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem,
             attr[1].id = cudaLaunchAttributeCooperative;
             attr[1].val.cooperative = 1;
             cfg.attrs = attr;
-            // OPN_NO_COOP_CLUSTER=1: plain cluster launch (Nsight Compute cannot replay cooperative cluster launches);
-            // the grid never exceeds the co-resident capacity computed above, the time-outs cover the rest
-            const char* e = getenv("OPN_NO_COOP_CLUSTER");
-            cfg.numAttrs = (e && e[0] == '1') ? 1 : 2;
-            OPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+            // Nsight Compute cannot replay cooperative cluster launches (the driver's own ncu pass of round 1 died on this
+            // kernel).  The cooperative attribute only asks the driver to verify co-residency -- the grid never exceeds
+            // the capacity computed above and every wait has a time-out -- so it is dropped when a profiler is injected
+            // (CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_PERFWORKS_DIR are set by ncu for its target), when
+            // OPN_NO_COOP_CLUSTER=1 asks for it, or after a cooperative launch has been refused once.
+            static int plain_cluster = -1;
+            if (plain_cluster < 0) {
+                const char* e = getenv("OPN_NO_COOP_CLUSTER");
+                plain_cluster = ((e && e[0] == '1') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) ? 1 : 0;
+            }
+            cfg.numAttrs = plain_cluster ? 1 : 2;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, p);
+            if (le != cudaSuccess && !plain_cluster) {
+                (void)cudaGetLastError();
+                plain_cluster = 1;
+                cfg.numAttrs = 1;
+                le = cudaLaunchKernelEx(&cfg, kernel, p);
+            }
+            OPN_CUDA(le);
         } else {
             void* args[] = {(void*)&p};
             OPN_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(n_slices * ng), dim3(threads), args, smem,

@@ -40,35 +40,63 @@ def shard_bounds(global_batch: int, rank: int, world: int):
 class FlatGradAllReducer:
     """Averages the gradients of `params` across ranks with a single collective.
 
-    After ``reduce()`` every ``p.grad`` is a view into one contiguous fp32 buffer holding the
-    rank-averaged gradient, so the optimiser sees identical values on every rank."""
+    The flat fp32 buffer exists from construction and its slices are registered as the landing slots of the weight
+    gradients (``ops.register_grad_slots``): the backward kernels write into it directly, so ``reduce()`` is the
+    all-reduce alone (``ncclAvg`` on NCCL: no scaling pass either) plus a copy for any gradient that did not land in its
+    slot (a transposed product, an accumulated gradient).  After ``reduce()`` every ``p.grad`` is a view into the buffer
+    holding the rank-averaged gradient, so the optimiser sees identical values on every rank."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         self.numel = sum(p.numel() for p in self.params)
-        self.flat: Optional[torch.Tensor] = None
+        dev = self.params[0].device
+        self.flat: torch.Tensor = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self._views: List[torch.Tensor] = []
+        off = 0
+        for p in self.params:
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
         self.collectives = 0
+        self.copies = 0          # gradients that had to be copied into their slot (statistics)
+        if dev.type == "cuda":
+            from . import ops
+            ops.register_grad_slots(self.params, self.flat)
+
+    def close(self) -> None:
+        """Forget the landing slots (the buffer stays valid for whoever still holds views of it)."""
+        if self.flat.device.type == "cuda":
+            from . import ops
+            ops.unregister_grad_slots(self.params)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
 
     @property
     def nbytes(self) -> int:
         return 4 * self.numel
 
     def reduce(self) -> torch.Tensor:
-        grads = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
-        if self.flat is None or self.flat.device != grads[0].device:
-            self.flat = torch.empty(self.numel, dtype=torch.float32, device=grads[0].device)
-        torch.cat(grads, out=self.flat)
+        for p, view in zip(self.params, self._views):
+            g = p.grad
+            if g is None:
+                view.zero_()
+            elif g.data_ptr() != view.data_ptr() or not g.is_contiguous():
+                view.copy_(g)
+                self.copies += 1
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / world)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:   # gloo has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / world)
             self.collectives += 1
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        for p, view in zip(self.params, self._views):
+            p.grad = view
         return self.flat
 
 

@@ -83,6 +83,35 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
             break
 
 
+# ---- gradient landing slots ---------------------------------------------------------------------------------------------
+# A data-parallel reducer / flat optimiser registers, per parameter, the slice of its flat gradient buffer; the backward
+# functions below then write weight gradients straight into those slices (autograd adopts the tensor as p.grad when p.grad
+# is None), so no concatenation pass runs before the all-reduce.
+_grad_slots = {}
+
+
+def register_grad_slots(params, flat: torch.Tensor) -> None:
+    """`flat`: 1-D fp32 buffer holding the gradients of `params` back to back in that order."""
+    off = 0
+    for p in params:
+        _grad_slots[p.data_ptr()] = (flat, off, tuple(p.shape))
+        off += p.numel()
+
+
+def unregister_grad_slots(params) -> None:
+    for p in params:
+        _grad_slots.pop(p.data_ptr(), None)
+
+
+def _grad_like(weight: torch.Tensor) -> torch.Tensor:
+    """Uninitialised tensor for the gradient of `weight`: its registered flat-buffer slice, else a fresh allocation."""
+    slot = _grad_slots.get(weight.data_ptr())
+    if slot is not None and slot[2] == tuple(weight.shape) and slot[0].device == weight.device:
+        flat, off, shape = slot
+        return flat[off:off + weight.numel()].view(shape)
+    return torch.empty_like(weight)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -235,7 +264,7 @@ class LinearFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             sgemm(dy, weight, dx, trans_a=False, trans_b=False, M=M, N=K, K=N, lda=N, ldb=K, ldc=K)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(weight)
+            dw = _grad_like(weight)
             sgemm(dy, x, dw, trans_a=True, trans_b=False, M=N, N=K, K=M, lda=N, ldb=K, ldc=K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(N, device=x.device, dtype=torch.float32)
@@ -336,10 +365,10 @@ def _lstm_weight_grads(dgates, x, hs, w_ih, w_hh, need_dw_ih, need_dw_hh):
     H = w_hh.shape[1]
     dw_ih = dw_hh = None
     if need_dw_ih:
-        dw_ih = torch.empty_like(w_ih)
+        dw_ih = _grad_like(w_ih)
         sgemm(dgates, x, dw_ih, trans_a=True, trans_b=False, M=4 * H, N=I, K=B * T, lda=4 * H, ldb=I, ldc=I)
     if need_dw_hh:
-        dw_hh = torch.empty_like(w_hh)
+        dw_hh = _grad_like(w_hh)
         if T > 1:
             # dW_hh = sum_{b, t>=1} dgates[b,t]^T hs[b,t-1].  Contract the flat row pairs (r+1, r) over all
             # B*T-1 rows, then take out the B-1 pairs that straddle two videos (rows b*T and b*T-1).

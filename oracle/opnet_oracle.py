@@ -147,7 +147,7 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tenso
     return (x - mu) / torch.sqrt(var + LN_EPS) * w + b
 
 
-def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int, drop=None) -> torch.Tensor:
+def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int, drop=None, q_chunk: Optional[int] = None) -> torch.Tensor:
     """One post-norm encoder layer over x [S, N, D] (sequence-first, N independent
     columns).  Restates nn.TransformerEncoderLayer as built at
     learned_models.py:166 (d_model=D, nhead, defaults otherwise).
@@ -156,7 +156,10 @@ def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int, drop=None
     nn.Dropout sites in execution order -- "<prefix>.attn" (attention weights [N,nhead,S,S], after the softmax),
     "<prefix>.dropout1" (the attention block's output [S,N,D]), "<prefix>.dropout" (after the ReLU, [S,N,2048]),
     "<prefix>.dropout2" ([S,N,D]) -- and applies whatever mask the caller pins (tests: the counter-based mask of
-    oracle/dropout_mask.py; PyTorch's own random stream cannot be pinned)."""
+    oracle/dropout_mask.py; PyTorch's own random stream cannot be pinned).
+
+    ``q_chunk``: evaluate the attention in blocks of that many query rows (the same arithmetic per row; the [S,S] score
+    matrix of BASELINE config 3, S = 9600, is 1.5 GB per head in fp64 -- in blocks it fits any host)."""
     if drop is None:
         drop = lambda site, t: t
     S, N, D = x.shape
@@ -168,8 +171,15 @@ def encoder_layer(x: torch.Tensor, p: Params, prefix: str, nhead: int, drop=None
         return z.reshape(S, N, nhead, dh).permute(1, 2, 0, 3)
 
     q, k, v = heads(q), heads(k), heads(v)
-    scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
-    attn = drop(f"{prefix}.attn", torch.softmax(scores, dim=-1)) @ v   # [N,nhead,S,dh]
+    if q_chunk is None:
+        scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+        attn = drop(f"{prefix}.attn", torch.softmax(scores, dim=-1)) @ v   # [N,nhead,S,dh]
+    else:
+        blocks = []
+        for s0 in range(0, S, q_chunk):
+            sc = (q[:, :, s0:s0 + q_chunk] @ k.transpose(-1, -2)) / math.sqrt(dh)
+            blocks.append(drop(f"{prefix}.attn", torch.softmax(sc, dim=-1)) @ v)
+        attn = torch.cat(blocks, dim=2)
     attn = attn.permute(2, 0, 1, 3).reshape(S, N, D)
     attn = attn @ p[f"{prefix}.self_attn.out_proj.weight"].t() + p[f"{prefix}.self_attn.out_proj.bias"]
     x = layer_norm(x + drop(f"{prefix}.dropout1", attn), p[f"{prefix}.norm1.weight"], p[f"{prefix}.norm1.bias"])
@@ -219,7 +229,7 @@ def non_linear_lstm_forward(p: Params, x: torch.Tensor, fast: bool = False):
 
 
 def transformer_lstm_forward(p: Params, x: torch.Tensor, config: Dict[str, int], fast: bool = False,
-                             all_slots: bool = False, drop=None):
+                             all_slots: bool = False, drop=None, q_chunk: Optional[int] = None):
     """learned_models.py:174-197; eval mode unless ``drop`` pins the dropout masks (see encoder_layer).
 
     ``all_slots=True`` evaluates the encoder on the full (B*T, 15, D) tensor exactly as
@@ -233,7 +243,7 @@ def transformer_lstm_forward(p: Params, x: torch.Tensor, config: Dict[str, int],
     if not all_slots:
         seq = seq[:, :1, :]
     for i in range(config["num_attention_layers"]):
-        seq = encoder_layer(seq, p, f"attention_encoder.layers.{i}", nhead, drop)
+        seq = encoder_layer(seq, p, f"attention_encoder.layers.{i}", nhead, drop, q_chunk)
     snitch = seq[:, 0, :].reshape(B, T, -1)
     h = lstm_stack(snitch, p, "video_LSTM", config["num_lstm_layers"], fast)
     return h @ p["predictions_layer.weight"].t()

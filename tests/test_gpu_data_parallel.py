@@ -54,6 +54,15 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.synchronize()
     assert reducer.collectives == 1
     torch.save(flat.cpu(), os.path.join(out_dir, f"flat{rank}.pt"))
+    # second step with the reducer in place: the weight gradients land in the flat buffer directly (no concatenation);
+    # only the transposed dW_pred product is copied into its slot
+    copies = reducer.copies
+    _grads(model, boxes[lo:hi], labels[lo:hi], dev)
+    landed = sum(p.grad.data_ptr() == v.data_ptr() for p, v in zip(reducer.params, reducer._views))
+    flat2 = reducer.reduce().clone()
+    torch.cuda.synchronize()
+    assert landed >= len(reducer.params) - 1 and reducer.copies - copies <= 1, (landed, reducer.copies - copies)
+    assert torch.equal(flat2.cpu(), torch.load(os.path.join(out_dir, f"flat{rank}.pt")))
     dist.destroy_process_group()
 
 

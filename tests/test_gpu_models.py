@@ -194,6 +194,31 @@ def test_transformer_lstm_shipped_config_small_batch(cuda_device):
     _oracle_vs_module("transformer_lstm", cfg, 2, 300, cuda_device, seed=8, grad_tol=2e-3)
 
 
+def test_transformer_lstm_baseline_config_3_full_shape(cuda_device):
+    """BASELINE.json configs[2] at its real shape: transformer_lstm, shipped JSON config, [B=32, T=300] -> one attention
+    sequence of S = 9600 rows, eval mode.  Forward against the fp64 slot-0 oracle evaluated in query blocks (the reference
+    itself cannot run this shape on a 62 GB host: it materialises 15 slots x 2 heads of [9600, 9600] scores); predicted
+    boxes within 1e-4, mean IoU equal to 3 decimals.  Gradients through the encoder are checked at S = 600 / 2400."""
+    cfg = {"boxes_features_dim": 256, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2,
+           "lstm_hidden_dim": 512}
+    B, T = 32, 300
+    boxes_np, labels_np, _ = make_batch(B, T, 5, seed=1234 + 9)
+    boxes = torch.from_numpy(boxes_np)
+    params = oracle.init_params("transformer_lstm", cfg, seed=9)
+    with torch.no_grad():
+        y_ref = oracle.transformer_lstm_forward({k: v.double() for k, v in params.items()}, boxes.double(), cfg, fast=True,
+                                                q_chunk=1200)
+    model = ModelsFactory.get_model("transformer_lstm", cfg)
+    model.load_state_dict(params)
+    model = model.to(cuda_device).eval()
+    with torch.no_grad():
+        y = model(boxes.to(cuda_device)).cpu()
+    dy = (y.double() - y_ref).abs().max().item()
+    print(f"\n[transformer_lstm B=32 T=300, S=9600] bbox max-abs {dy:.2e}")
+    assert dy <= BBOX_TOL, dy
+    assert round(oracle.mean_iou(y.numpy(), labels_np), 3) == round(oracle.mean_iou(y_ref.numpy().astype(np.float32), labels_np), 3)
+
+
 def test_transformer_lstm_train_mode_applies_dropout(cuda_device):
     """The reference's encoder layers carry nn.Dropout(p=0.1) at four sites (baselines/learned_models.py:166).  The
     mask stream is this library's own (ops.dropout), so the check is behavioural: train mode differs from eval mode

@@ -112,3 +112,14 @@ def test_oracle_dropout_sites_match_the_torch_encoder_layer():
     got = oracle.encoder_layer(x, params, "L", nhead, drop)
     assert seen == ["L.attn", "L.dropout1", "L.dropout", "L.dropout2"]
     assert (got - want).abs().max().item() < 1e-12
+
+
+def test_oracle_attention_in_query_blocks_is_the_same_function():
+    """q_chunk (used for BASELINE config 3 at S = 9600 on the GPU box) must not change the restatement."""
+    cfg = {"boxes_features_dim": 32, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 1, "lstm_hidden_dim": 32}
+    from objectpermanence_b200.synthetic import make_batch
+    boxes = torch.from_numpy(make_batch(3, 7, 5, seed=3)[0]).double()
+    params = {k: v.double() for k, v in oracle.init_params("transformer_lstm", cfg, seed=1).items()}
+    full = oracle.transformer_lstm_forward(params, boxes, cfg)
+    blocked = oracle.transformer_lstm_forward(params, boxes, cfg, q_chunk=5)
+    assert (full - blocked).abs().max().item() < 1e-14
