@@ -172,6 +172,22 @@ OPN_API int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1, int64_t H2, const fl
                   const float* cells1, const float* gates2, const float* cells2, const float* d_hs2, float* d_gates1,
                   float* d_gates2, float* d_logits, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- fused self-attention (transformer_lstm encoder) -----------------------------------
+ * softmax(Q K^T / sqrt(d)) V per head over ONE sequence of S rows, as nn.MultiheadAttention computes it inside
+ * nn.TransformerEncoderLayer (baselines/learned_models.py:166-168,184; the sequence axis of the reference is B*T).
+ *   qkv [S, 3D] packed q|k|v (in_proj output), nhead heads of d = D / nhead = 128 (OPN_ERR_UNSUPPORTED otherwise)
+ *   -> ctx [S, D].  No [S,S] tensor is formed: flash-style tcgen05 kernels (opn_attention_tc.cu); the backward pass
+ *   recomputes the scores from the row statistics the forward call leaves in `workspace`, which must therefore be
+ *   handed unchanged from opn_attention_fwd to opn_attention_bwd of the same call.
+ *   p_drop > 0: attention-weight dropout with the mask of opn_dropout (element (q,k) of head h = element q*S + k of the
+ *   stream (seed, offset + h * ceil(S*S/4))). */
+OPN_API int64_t opn_attention_workspace_bytes(int64_t S, int64_t D, int64_t nhead);
+OPN_API int opn_attention_fwd(int64_t S, int64_t D, int64_t nhead, const float* qkv, float* ctx, void* workspace,
+                      int64_t workspace_bytes, float p_drop, uint64_t seed, uint64_t offset, void* stream);
+OPN_API int opn_attention_bwd(int64_t S, int64_t D, int64_t nhead, const float* ctx, const float* d_ctx, float* d_qkv,
+                      void* workspace, int64_t workspace_bytes, float p_drop, uint64_t seed, uint64_t offset,
+                      void* stream);
+
 /* ---- element-wise / row-wise helpers (transformer_lstm encoder, MLP variant) -------- */
 /* dy[i] = (y[i] > 0) ? dy[i] : 0   (ReLU backward, in place on dy) */
 OPN_API int opn_relu_bwd(int64_t n, const float* y, float* dy, void* stream);

@@ -38,6 +38,9 @@ SIGNATURES = {
     "opn_opnet_fwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 16 + [c_int64, _P]),
     "opn_opnet_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "opn_opnet_bwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 15 + [c_int64, _P]),
+    "opn_attention_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "opn_attention_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, _P]),
+    "opn_attention_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, _P]),
     "opn_wtt_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "opn_wtt_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "opn_relu_bwd": (c_int, [c_int64, _P, _P, _P]),

@@ -450,7 +450,9 @@ __global__ void __launch_bounds__(TCT, 1) lstm_fwd_tc_kernel(const __grid_consta
 }
 
 // ======================================================= backward ======================================================
-template <int H, int PASSES>
+// RED: the reduce-scatter of the partial products is done by the L2 (vector atomic adds into one [128 x 16] accumulation
+// block per consumer and slot, zeroed by its consumer after reading) instead of by the consumer summing H/16 stored blocks
+template <int H, int PASSES, bool RED>
 __global__ void __launch_bounds__(TCT, 1) lstm_bwd_tc_kernel(const TcBwdParams p) {
     constexpr int PL = PASSES == 3 ? 2 : 1, NSL = H / UC, NHALF = H / 256;
     constexpr int W_PLANE = H * 128;
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(TCT, 1) lstm_bwd_tc_kernel(const TcBwdParams p
     const uint32_t tmem_base = tmem_base_s;
     Waiter wait = {&abort_flag, p.status, 0};
     constexpr size_t kBlock = (size_t)MV * UC;                         // floats of one (consumer, producer) block
-    constexpr size_t kSlot = (size_t)NSL * NSL * kBlock;               // floats per slot and group
+    constexpr size_t kSlot = (size_t)NSL * (RED ? 1 : NSL) * kBlock;   // floats per slot and group
     float* ring_g = p.ring + (size_t)group * 2 * kSlot;
     unsigned int* counter = p.counters + group;
 
@@ -563,12 +565,21 @@ __global__ void __launch_bounds__(TCT, 1) lstm_bwd_tc_kernel(const TcBwdParams p
                 if (!ok) dead = true;
                 TPH(1);
                 // block (consumer, producer): [4 float4 groups][128 videos][4 floats] -- lane = video, 512 contiguous bytes per warp load
-                const float* src = ring_g + (size_t)((s - 1) & 1) * kSlot + (size_t)slice * NSL * kBlock + (size_t)(2 * hf) * (MV * 4) + (size_t)v * 4;
+                if constexpr (RED) {
+                    float* src = ring_g + (size_t)((s - 1) & 1) * kSlot + (size_t)slice * kBlock + (size_t)(2 * hf) * (MV * 4) + (size_t)v * 4;
+                    acc0 = ld_cg4(src), acc1 = ld_cg4(src + MV * 4);
+                    // hand the block back zeroed: the producers add into this slot again two steps from now, after they
+                    // have acquired the counter this thread releases at the end of the step
+                    *reinterpret_cast<float4*>(src) = zero4;
+                    *reinterpret_cast<float4*>(src + MV * 4) = zero4;
+                } else {
+                    const float* src = ring_g + (size_t)((s - 1) & 1) * kSlot + (size_t)slice * NSL * kBlock + (size_t)(2 * hf) * (MV * 4) + (size_t)v * 4;
 #pragma unroll 8      // 16 loads in flight per thread; 32 (unroll 16) ran 1.8x slower: 12880 against 7266 clocks for this phase
-                for (int pr = 0; pr < NSL; ++pr) {
-                    const float4 x0 = ld_cg4(src + (size_t)pr * kBlock), x1 = ld_cg4(src + (size_t)pr * kBlock + MV * 4);
-                    acc0.x += x0.x, acc0.y += x0.y, acc0.z += x0.z, acc0.w += x0.w;
-                    acc1.x += x1.x, acc1.y += x1.y, acc1.z += x1.z, acc1.w += x1.w;
+                    for (int pr = 0; pr < NSL; ++pr) {
+                        const float4 x0 = ld_cg4(src + (size_t)pr * kBlock), x1 = ld_cg4(src + (size_t)pr * kBlock + MV * 4);
+                        acc0.x += x0.x, acc0.y += x0.y, acc0.z += x0.z, acc0.w += x0.w;
+                        acc1.x += x1.x, acc1.y += x1.y, acc1.z += x1.z, acc1.w += x1.w;
+                    }
                 }
             }
             TPH(2);
@@ -640,7 +651,7 @@ __global__ void __launch_bounds__(TCT, 1) lstm_bwd_tc_kernel(const TcBwdParams p
             if (!dead && !wait.barrier(&acc_full, (uint32_t)s & 1u)) dead = true;
             tc::fence_after();
             TPH(4);
-            float* dst = ring_g + (size_t)(s & 1) * kSlot + (size_t)slice * kBlock + (size_t)v * 4;
+            float* dst = ring_g + (size_t)(s & 1) * kSlot + (RED ? (size_t)0 : (size_t)slice * kBlock) + (size_t)v * 4;
             const int col0 = hf * (H / 2);
 #pragma unroll 2
             for (int col = col0; col < col0 + H / 2; col += 32) {
@@ -649,12 +660,16 @@ __global__ void __launch_bounds__(TCT, 1) lstm_bwd_tc_kernel(const TcBwdParams p
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int cb = 0; cb < 2; ++cb) {     // two consumers of 16 units per 32 columns
-                    float* o = dst + (size_t)(col / UC + cb) * NSL * kBlock;
+                    float* o = dst + (size_t)(col / UC + cb) * (RED ? 1 : NSL) * kBlock;
 #pragma unroll
-                    for (int j = 0; j < UC / 4; ++j)
-                        *reinterpret_cast<float4*>(o + (size_t)j * (MV * 4)) =
-                            make_float4(__uint_as_float(x[16 * cb + 4 * j]) * inv, __uint_as_float(x[16 * cb + 4 * j + 1]) * inv,
-                                        __uint_as_float(x[16 * cb + 4 * j + 2]) * inv, __uint_as_float(x[16 * cb + 4 * j + 3]) * inv);
+                    for (int j = 0; j < UC / 4; ++j) {
+                        const float y0 = __uint_as_float(x[16 * cb + 4 * j]) * inv, y1 = __uint_as_float(x[16 * cb + 4 * j + 1]) * inv;
+                        const float y2 = __uint_as_float(x[16 * cb + 4 * j + 2]) * inv, y3 = __uint_as_float(x[16 * cb + 4 * j + 3]) * inv;
+                        if constexpr (RED)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + (size_t)j * (MV * 4)), "f"(y0), "f"(y1), "f"(y2), "f"(y3) : "memory");
+                        else
+                            *reinterpret_cast<float4*>(o + (size_t)j * (MV * 4)) = make_float4(y0, y1, y2, y3);
+                    }
                 }
             }
             tc::fence_before();
@@ -744,21 +759,23 @@ int run_fwd_tc(const FwdParams& p0, int64_t B, char* ws, cudaStream_t s) {
     return OPN_OK;
 }
 
-template <int H, int PASSES>
+template <int H, int PASSES, bool RED>
 int run_bwd_tc(const BwdParams& p0, int64_t B, char* ws, cudaStream_t s) {
     constexpr int PL = PASSES == 3 ? 2 : 1, NSL = H / UC;
     constexpr size_t smem = 1024 + (size_t)PL * H * 128 + (size_t)PL * A_TILE;
     const TcLayout l = tc_layout(B, H);
     const int groups = (int)((B + MV - 1) / MV);
     int cap = 0;
-    int rc = tc_capacity(lstm_bwd_tc_kernel<H, PASSES>, smem, &cap);
+    int rc = tc_capacity(lstm_bwd_tc_kernel<H, PASSES, RED>, smem, &cap);
     if (rc != OPN_OK) return rc;
     const int per_launch = cap / NSL;
     if (per_launch < 1) {
         set_error("lstm_bwd (tcgen05): device cannot co-schedule %d CTAs (capacity %d)", NSL, cap);
         return OPN_ERR_UNSUPPORTED;
     }
-    OPN_CUDA(cudaMemsetAsync(ws, 0, l.ring_off, s));     // status + counters; the ring is written before it is read
+    // status + counters; the stored-block ring is written before it is read, the accumulation blocks of the RED flavour
+    // (2 slots x H/16 consumers x [128 x 16] floats per group) start from zero
+    OPN_CUDA(cudaMemsetAsync(ws, 0, l.ring_off + (RED ? (size_t)groups * 2 * NSL * MV * UC * sizeof(float) : 0), s));
     TcBwdParams p;
     p.w_hh = p0.w_hh, p.gates = p0.gates, p.cells = p0.cells, p.dh_out = p0.dh_out, p.dgates = p0.dgates;
     p.ring = reinterpret_cast<float*>(ws + l.ring_off);
@@ -769,7 +786,7 @@ int run_bwd_tc(const BwdParams& p0, int64_t B, char* ws, cudaStream_t s) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
         void* args[] = {(void*)&p};
-        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_tc_kernel<H, PASSES>, dim3(NSL * ng), dim3(TCT), args, smem, s));
+        OPN_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_bwd_tc_kernel<H, PASSES, RED>, dim3(NSL * ng), dim3(TCT), args, smem, s));
         count_launch();
     }
     return OPN_OK;
@@ -803,8 +820,17 @@ int lstm_fwd_tc(const FwdParams& p, int64_t B, int64_t H, void* workspace, cudaS
 int lstm_bwd_tc(const BwdParams& p, int64_t B, int64_t H, void* workspace, cudaStream_t s) {
     char* ws = static_cast<char*>(workspace);
     const bool single = current_precision() == 1;
-    if (H == 512) return single ? run_bwd_tc<512, 1>(p, B, ws, s) : run_bwd_tc<512, 3>(p, B, ws, s);
-    return single ? run_bwd_tc<256, 1>(p, B, ws, s) : run_bwd_tc<256, 3>(p, B, ws, s);
+    static int red = -1;     // OPN_LSTM_TC_RED=0: the consumers sum stored blocks (the first version)
+    if (red < 0) {
+        const char* e = getenv("OPN_LSTM_TC_RED");
+        red = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (red) {
+        if (H == 512) return single ? run_bwd_tc<512, 1, true>(p, B, ws, s) : run_bwd_tc<512, 3, true>(p, B, ws, s);
+        return single ? run_bwd_tc<256, 1, true>(p, B, ws, s) : run_bwd_tc<256, 3, true>(p, B, ws, s);
+    }
+    if (H == 512) return single ? run_bwd_tc<512, 1, false>(p, B, ws, s) : run_bwd_tc<512, 3, false>(p, B, ws, s);
+    return single ? run_bwd_tc<256, 1, false>(p, B, ws, s) : run_bwd_tc<256, 3, false>(p, B, ws, s);
 }
 
 }  // namespace opn

@@ -645,6 +645,42 @@ class AddLayerNormFn(torch.autograd.Function):
         return dx, dx, dw, db, None
 
 
+class FusedSelfAttentionFn(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(d)) V per head over ONE sequence of S rows, head dimension 128, as fused flash-style tcgen05
+    kernels (csrc/opn_attention_tc.cu): no [S,S] tensor, the backward pass recomputes the scores from the row statistics
+    kept in the workspace.  Same arguments and dropout stream as SelfAttentionFn (the materialised form, kept for other
+    head dimensions and for A/B: OPN_ATTENTION=materialized)."""
+
+    @staticmethod
+    def forward(ctx, qkv, nhead: int, p_drop: float = 0.0, seed: int = 0, offset: int = 0):
+        _require_cuda(qkv)
+        qkv = qkv.contiguous()
+        S, D3 = qkv.shape
+        D = D3 // 3
+        lib = _lib.load()
+        out = torch.empty(S, D, device=qkv.device, dtype=torch.float32)
+        ws = torch.empty(lib.opn_attention_workspace_bytes(S, D, nhead), dtype=torch.uint8, device=qkv.device)
+        rc = lib.opn_attention_fwd(S, D, nhead, qkv.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), float(p_drop),
+                                   int(seed), int(offset), _stream())
+        _lib.check(rc, "opn_attention_fwd")
+        _lstm_check(qkv.device, "opn_attention_fwd")
+        ctx.save_for_backward(out, ws)
+        ctx.args = (S, D, nhead, float(p_drop), int(seed), int(offset))
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        out, ws = ctx.saved_tensors
+        S, D, nhead, p_drop, seed, offset = ctx.args
+        dctx = dctx.contiguous()
+        dqkv = torch.empty(S, 3 * D, device=out.device, dtype=torch.float32)
+        rc = _lib.load().opn_attention_bwd(S, D, nhead, out.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), p_drop, seed, offset, _stream())
+        _lib.check(rc, "opn_attention_bwd")
+        _lstm_check(out.device, "opn_attention_bwd")
+        return dqkv, None, None, None, None
+
+
 class SelfAttentionFn(torch.autograd.Function):
     """softmax(Q K^T / sqrt(d)) V per head over ONE sequence of S rows.
 
@@ -803,6 +839,8 @@ def add_layer_norm(x, res, weight, bias, eps: float = 1e-5):
 
 def self_attention(qkv, nhead: int, p_drop: float = 0.0, seed: int = 0, offset: int = 0):
     """p_drop > 0: attention-weight dropout with the mask of (seed, offset); one head consumes (S*S+3)//4 blocks."""
+    if qkv.shape[-1] // 3 == 128 * nhead and os.environ.get("OPN_ATTENTION", "fused") != "materialized":
+        return FusedSelfAttentionFn.apply(qkv, nhead, p_drop, seed, offset)
     return SelfAttentionFn.apply(qkv, nhead, p_drop, seed, offset)
 
 

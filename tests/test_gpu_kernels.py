@@ -447,6 +447,34 @@ def test_self_attention(cuda_device, S, D, nhead):
     assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("S,nhead", [(1, 1), (12, 2), (64, 1), (130, 2), (333, 1), (600, 2), (1000, 1)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_fused_attention_head_dim_128(cuda_device, S, nhead, p_drop):
+    """The flash-style tcgen05 kernels (head dimension 128: the shipped transformer_lstm config) against plain fp64 math:
+    ragged S (tail tiles of both the 128-row and the 64-row tilings), one and two heads, with and without attention-weight
+    dropout (mask from the oracle's restatement of the generator); output and the gradient of the packed q|k|v."""
+    from oracle import dropout_mask
+    D, d = 128 * nhead, 128
+    seed, offset = 4242, 77
+    qkv, dctx = _rand((S, 3 * D), 81 + S), _rand((S, D), 82 + S)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = [z.reshape(S, nhead, d).permute(1, 0, 2) for z in (qr[:, :D], qr[:, D:2 * D], qr[:, 2 * D:])]
+    probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    if p_drop > 0:
+        blocks = (S * S + 3) // 4
+        keep = torch.stack([torch.from_numpy(dropout_mask.keep_mask(S * S, p_drop, seed, offset + h * blocks)).reshape(S, S)
+                            for h in range(nhead)])
+        probs = probs * keep.double() / (1.0 - p_drop)
+    ref = (probs @ v).permute(1, 0, 2).reshape(S, D)
+    ref.backward(dctx.double())
+    qg = qkv.to(cuda_device).requires_grad_(True)
+    out = ops.self_attention(qg, nhead, p_drop, seed, offset)
+    assert out.grad_fn.__class__.__name__.startswith("FusedSelfAttentionFn")
+    out.backward(dctx.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
+    assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4 * max(1.0, qr.grad.abs().max().item())
+
+
 # ---- dropout (train mode of the encoder layer) ------------------------------------------------
 @pytest.mark.parametrize("n,p,seed,offset", [(1, 0.1, 1, 0), (4, 0.1, 7, 3), (1027, 0.1, 1234, 0), (65536, 0.5, 2 ** 40 + 5, 2 ** 33),
                                               (100003, 0.0, 9, 11), (300 * 300 + 1, 0.9, 3, 12345)])

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider -k "fused_attention" --tb=line > gpurun_out/r02_19_attn_tests.log 2>&1; tail -25 gpurun_out/r02_19_attn_tests.log | cut -c1-250

@@ -14,6 +14,7 @@ from objectpermanence_b200.training import TrainingStep
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--model", default="opnet")
 ap.add_argument("--tc", action="store_true", help="one H=512 LSTM layer at B=256 through the batch-wide tcgen05 kernels")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -30,12 +31,14 @@ if args.tc:
     print("launches", _lib.launch_count())
 else:
     cfg = {"object_to_track_pred_dim": 15, "object_to_track_hidden_dim": 256, "videos_hidden_dim": 512}
+    if args.model == "transformer_lstm":
+        cfg = {"boxes_features_dim": 256, "num_attention_heads": 2, "num_attention_layers": 2, "num_lstm_layers": 2, "lstm_hidden_dim": 512}
     torch.manual_seed(0)
-    model = ModelsFactory.get_model("opnet", cfg).to(dev).train()
-    step = TrainingStep(model, "opnet")
-    b, l, _ = make_batch(args.batch, 300, 6, seed=1234)
+    model = ModelsFactory.get_model(args.model, cfg).to(dev).train()
+    step = TrainingStep(model, args.model)
+    b, l, _ = make_batch(args.batch, 300, 5 if args.model == "transformer_lstm" else 6, seed=1234)
     b, l = torch.from_numpy(b).to(dev), torch.from_numpy(l).to(dev)
-    for _ in range(5):
+    for _ in range(2 if args.model == "transformer_lstm" else 5):
         step.forward_backward(b, l)
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
