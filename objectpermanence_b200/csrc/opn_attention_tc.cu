@@ -53,7 +53,35 @@ struct AttnParams {
     unsigned int drop_threshold;   // keep when word >= threshold; 0 = no dropout
     float drop_scale;
     unsigned long long seed, offset;
+    // work split (see plan_split): CTAs [0, n_full) own a whole row of streamed tiles of one (resident tile, head); every
+    // leftover (resident tile, head) is cut into `segs` segments of consecutive streamed tiles, one CTA each, whose partial
+    // accumulators go to `part` and are merged by the combine kernels
+    float* part;             // [slot][2][128][128]
+    float* part_ml;          // [slot][2][128]   forward: reference maximum and sum of exponentials of a segment
+    int n_rtiles, n_full, segs, grid;
 };
+
+struct Work {
+    int rt, h;       // resident tile and head
+    int j0, nt;      // first streamed tile and their number
+    int slot;        // partial-accumulator slot, -1: the CTA owns the whole row and writes the result itself
+};
+__device__ __forceinline__ Work my_work(const AttnParams& p, int n_tiles) {
+    Work w;
+    const int b = (int)blockIdx.x;
+    int row;
+    if (b < p.n_full) {
+        row = b, w.j0 = 0, w.nt = n_tiles, w.slot = -1;
+    } else {
+        const int k = b - p.n_full, sg = k % p.segs;
+        row = p.n_full + k / p.segs;
+        w.j0 = (int)((long long)sg * n_tiles / p.segs);
+        w.nt = (int)((long long)(sg + 1) * n_tiles / p.segs) - w.j0;
+        w.slot = k;
+    }
+    w.rt = row % p.n_rtiles, w.h = row / p.n_rtiles;
+    return w;
+}
 
 // ---- operand planes: [tensor t (0 Q', 1 K, 2 V, 3 dO)][plane (hi, lo)][head][S_pad][128] bf16 ---------------------------
 __device__ __forceinline__ long long plane_row(const AttnParams& p, int t, int plane, int h, int row) {
@@ -114,7 +142,7 @@ __device__ __forceinline__ bool await(uint64_t* bar, uint32_t parity, unsigned i
             if (clock64() - t0 > kAttnTimeout) {
                 if (atomicCAS(status, 0u, 2u) == 0u) {
                     status[1] = blockIdx.x;
-                    status[2] = blockIdx.y;
+                    status[2] = 0u;
                     status[3] = threadIdx.x;
                 }
                 *abort_s = 1;
@@ -348,8 +376,9 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t kv_s = base;      // K/V stages: NST x (K tile, V tile)
     constexpr int NST = 3;
-    const int qt = blockIdx.x, h = blockIdx.y;
-    const int n_tiles = (p.S + TK - 1) / TK;
+    const Work wk = my_work(p, (p.S + TK - 1) / TK);
+    const int qt = wk.rt, h = wk.h, j0 = wk.j0;
+    const int n_tiles = wk.nt;      // streamed tiles of THIS CTA: key tiles j0 .. j0 + n_tiles - 1
 
     if (tid == 0) {
         mbar_init(&sh.res_full, 4);
@@ -382,7 +411,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1;
             if (j >= 2 && !await(&sh.rng_empty[b], ((uint32_t)(j >> 1) - 1u) & 1u, p.status, abort_s)) break;
-            keep_bits[b][r] = keep_bits_row((unsigned long long)(qt * TQ + r) * p.S + (unsigned long long)j * TK, p.seed, drop_off,
+            keep_bits[b][r] = keep_bits_row((unsigned long long)(qt * TQ + r) * p.S + (unsigned long long)(j0 + j) * TK, p.seed, drop_off,
                                             p.drop_threshold);
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh.rng_full[b]);
@@ -393,8 +422,8 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
                 const int st = j % NST;
                 if (j >= NST && !await(&sh.kv_empty[st], ((uint32_t)(j / NST) - 1u) & 1u, p.status, abort_s)) break;
                 mbar_arrive_expect_tx(&sh.kv_full[st], 2 * PL * 2 * BLK64);
-                load_tile<PL>(kv_s + st * 2 * STR_TILE, &map64, p, 1, h, j * TK, BLK64, &sh.kv_full[st]);
-                load_tile<PL>(kv_s + st * 2 * STR_TILE + STR_TILE, &map64, p, 2, h, j * TK, BLK64, &sh.kv_full[st]);
+                load_tile<PL>(kv_s + st * 2 * STR_TILE, &map64, p, 1, h, (j0 + j) * TK, BLK64, &sh.kv_full[st]);
+                load_tile<PL>(kv_s + st * 2 * STR_TILE + STR_TILE, &map64, p, 2, h, (j0 + j) * TK, BLK64, &sh.kv_full[st]);
             }
         }
     } else if (warp == 1) {
@@ -462,7 +491,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh.s_empty[sb]);
             APH(2);
-            const int kvalid = p.S - j * TK;      // keys of this tile that exist
+            const int kvalid = p.S - (j0 + j) * TK;      // keys of this tile that exist
             float mx = -INFINITY;
 #pragma unroll
             for (int i = 0; i < TK; ++i) {
@@ -526,14 +555,15 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
         if (tid == 64) APH_STORE(p.status, 0);
         if (ok && await(&sh.pv_full[(n_tiles - 1) & 1], (uint32_t)((n_tiles - 1) >> 1) & 1u, p.status, abort_s)) {
             tc::fence_after();
-            const float inv = 1.0f / l;
-            float* dst = p.ctx_out + (size_t)q * p.D + h * DH;
+            const bool whole = wk.slot < 0;      // a segment leaves its unnormalised output, reference maximum and sum
+            const float inv = whole ? 1.0f / l : 1.0f;
+            float* dst = whole ? p.ctx_out + (size_t)q * p.D + h * DH : p.part + ((size_t)wk.slot * 2 * TQ + r) * DH;
 #pragma unroll
             for (int c = 0; c < DH; c += 32) {
                 uint32_t x[32];
                 tc::tmem_ld32(lane_addr + 128 + c, x);
                 tc::tmem_ld_wait();
-                if (q < p.S) {
+                if (q < p.S || !whole) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
                         *reinterpret_cast<float4*>(dst + c + i) =
@@ -542,7 +572,12 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
                 }
             }
             tc::fence_before();
-            p.lse2[(size_t)h * p.S_pad + q] = (q < p.S) ? m + log2f(l) : INFINITY;
+            if (whole) {
+                p.lse2[(size_t)h * p.S_pad + q] = (q < p.S) ? m + log2f(l) : INFINITY;
+            } else {
+                p.part_ml[((size_t)wk.slot * 2 + 0) * TQ + r] = m;
+                p.part_ml[((size_t)wk.slot * 2 + 1) * TQ + r] = l;
+            }
         }
     }
     tc::fence_before();
@@ -563,8 +598,9 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ unsigned long long keep_bits[TQ];     // dropout keep bits of one tile (single buffer: 224 KB of tiles leave 3 KB)
     const uint32_t q_s = base, do_s = base + RES_TILE, k_s = base + 2 * RES_TILE, v_s = k_s + 2 * STR_TILE;
-    const int qt = blockIdx.x, h = blockIdx.y;
-    const int n_tiles = (p.S + TK - 1) / TK;
+    const Work wk = my_work(p, (p.S + TK - 1) / TK);
+    const int qt = wk.rt, h = wk.h, j0 = wk.j0;
+    const int n_tiles = wk.nt;      // key tiles j0 .. j0 + n_tiles - 1
 
     if (tid == 0) {
         mbar_init(&sh.res_full, 1);
@@ -597,7 +633,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
             unsigned long long bits[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half)
-                bits[half] = keep_bits_row((unsigned long long)(qt * TQ + (warp - 6) * 32 + lane + 64 * half) * p.S + (unsigned long long)j * TK,
+                bits[half] = keep_bits_row((unsigned long long)(qt * TQ + (warp - 6) * 32 + lane + 64 * half) * p.S + (unsigned long long)(j0 + j) * TK,
                                            p.seed, drop_off, p.drop_threshold);
             if (j >= 1 && !await(&sh.rng_empty[0], (uint32_t)(j - 1) & 1u, p.status, abort_s)) break;     // tile j-1's bits have been read
             keep_bits[(warp - 6) * 32 + lane] = bits[0];
@@ -615,10 +651,10 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
                 // K stage st was last read by dQ += dS K of tile j-2; V (single) by the score products of tile j-1
                 if (j >= 2 && !await(&sh.str_empty[st], ((uint32_t)(j >> 1) - 1u) & 1u, p.status, abort_s)) break;
                 mbar_arrive_expect_tx(&sh.str_full[st], PL * 2 * BLK64);
-                load_tile<PL>(k_s + st * STR_TILE, &map64, p, 1, h, j * TK, BLK64, &sh.str_full[st]);
+                load_tile<PL>(k_s + st * STR_TILE, &map64, p, 1, h, (j0 + j) * TK, BLK64, &sh.str_full[st]);
                 if (j >= 1 && !await(&sh.v_empty, (uint32_t)(j - 1) & 1u, p.status, abort_s)) break;
                 mbar_arrive_expect_tx(&sh.v_full, PL * 2 * BLK64);
-                load_tile<PL>(v_s, &map64, p, 2, h, j * TK, BLK64, &sh.v_full);
+                load_tile<PL>(v_s, &map64, p, 2, h, (j0 + j) * TK, BLK64, &sh.v_full);
             }
         }
     } else if (warp == 1) {
@@ -679,7 +715,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
                 tc::fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&sh.s_empty[sb]);
-                const int kvalid = p.S - j * TK;
+                const int kvalid = p.S - (j0 + j) * TK;
                 unsigned long long bits = ~0ull;
                 if (DROP) {
                     if (!await(&sh.rng_full[0], (uint32_t)j & 1u, p.status, abort_s)) { ok = false; break; }
@@ -705,18 +741,20 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
         }
         if (ok && await(&sh.pv_full[(n_tiles - 1) & 1], (uint32_t)((n_tiles - 1) >> 1) & 1u, p.status, abort_s)) {
             tc::fence_after();
-            float* dst = p.dqkv + (size_t)q * (3 * p.D) + h * DH;
+            const bool whole = wk.slot < 0;
+            const float mul = whole ? p.scale : 1.0f;
+            float* dst = whole ? p.dqkv + (size_t)q * (3 * p.D) + h * DH : p.part + ((size_t)wk.slot * 2 * TQ + r) * DH;
 #pragma unroll
             for (int c = 0; c < DH; c += 32) {
                 uint32_t x[32];
                 tc::tmem_ld32(lane_addr + 256 + c, x);
                 tc::tmem_ld_wait();
-                if (q < p.S) {
+                if (q < p.S || !whole) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
                         *reinterpret_cast<float4*>(dst + c + i) =
-                            make_float4(__uint_as_float(x[i]) * p.scale, __uint_as_float(x[i + 1]) * p.scale,
-                                        __uint_as_float(x[i + 2]) * p.scale, __uint_as_float(x[i + 3]) * p.scale);
+                            make_float4(__uint_as_float(x[i]) * mul, __uint_as_float(x[i + 1]) * mul,
+                                        __uint_as_float(x[i + 2]) * mul, __uint_as_float(x[i + 3]) * mul);
                 }
             }
             tc::fence_before();
@@ -743,8 +781,9 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
     const uint32_t k_s = base, v_s = base + RES_TILE, qd_s = base + 2 * RES_TILE;     // stages: (Q' tile, dO tile) x 1.5: see below
     // 224 KB: K 64 + V 64 + Q' 2 x 32 + dO 1 x 32 -- Q' double buffered (the TMA of the next tile overlaps), dO single
     const uint32_t do_s = qd_s + 2 * STR_TILE;
-    const int kt = blockIdx.x, h = blockIdx.y;
-    const int n_tiles = (p.S + TK - 1) / TK;     // query tiles of 64 rows
+    const Work wk = my_work(p, (p.S + TK - 1) / TK);
+    const int kt = wk.rt, h = wk.h, i0 = wk.j0;
+    const int n_tiles = wk.nt;     // query tiles of 64 rows: i0 .. i0 + n_tiles - 1
 
     if (tid == 0) {
         mbar_init(&sh.res_full, 1);
@@ -783,10 +822,10 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
                 const int key = kt * TQ + (warp - 6) * 32 + lane + 64 * half;
                 unsigned long long bits = 0ull;
                 if (shared_blocks) {
-                    bits = keep_bits_col_shared((unsigned long long)i * TK, p.S, key, lane, p.seed, drop_off, p.drop_threshold);
+                    bits = keep_bits_col_shared((unsigned long long)(i0 + i) * TK, p.S, key, lane, p.seed, drop_off, p.drop_threshold);
                 } else {
                     for (int c = 0; c < TK; ++c)
-                        if (keep_one((unsigned long long)(i * TK + c) * p.S + (unsigned long long)key, p.seed, drop_off, p.drop_threshold)) bits |= 1ull << c;
+                        if (keep_one((unsigned long long)((i0 + i) * TK + c) * p.S + (unsigned long long)key, p.seed, drop_off, p.drop_threshold)) bits |= 1ull << c;
                 }
                 out[half] = bits;
             }
@@ -805,10 +844,10 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
                 const int st = i & 1;
                 if (i >= 2 && !await(&sh.str_empty[st], ((uint32_t)(i >> 1) - 1u) & 1u, p.status, abort_s)) break;
                 mbar_arrive_expect_tx(&sh.str_full[st], PL * 2 * BLK64);
-                load_tile<PL>(qd_s + st * STR_TILE, &map64, p, 0, h, i * TK, BLK64, &sh.str_full[st]);
+                load_tile<PL>(qd_s + st * STR_TILE, &map64, p, 0, h, (i0 + i) * TK, BLK64, &sh.str_full[st]);
                 if (i >= 1 && !await(&sh.v_empty, (uint32_t)(i - 1) & 1u, p.status, abort_s)) break;     // dV += P^T dO of tile i-1 done
                 mbar_arrive_expect_tx(&sh.v_full, PL * 2 * BLK64);
-                load_tile<PL>(do_s, &map64, p, 3, h, i * TK, BLK64, &sh.v_full);
+                load_tile<PL>(do_s, &map64, p, 3, h, (i0 + i) * TK, BLK64, &sh.v_full);
             }
         }
     } else if (warp == 1) {
@@ -841,7 +880,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
         for (int i = 0; i < n_tiles; ++i) {
             // row statistics of the 64 queries of this tile (the named barriers order fill and use)
             {
-                const int qq = i * TK + (et & 63);
+                const int qq = (i0 + i) * TK + (et & 63);
                 const float v = (et < 64) ? p.lse2[(size_t)h * p.S_pad + qq] : p.delta[(size_t)h * p.S_pad + qq];
                 if (i > 0) asm volatile("bar.sync 2, 128;" ::: "memory");     // everybody is done with the previous tile's values
                 if (et < 64) lse_s[et] = v; else delta_s[et - 64] = v;
@@ -893,16 +932,17 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
         }
         if (!dead && await(&sh.done, (uint32_t)(n_tiles - 1) & 1u, p.status, abort_s)) {
             tc::fence_after();
-            float* dv = p.dqkv + (size_t)key * (3 * p.D) + 2 * p.D + h * DH;
-            float* dk = p.dqkv + (size_t)key * (3 * p.D) + p.D + h * DH;
-            const float kmul = 1.0f / kLog2e;     // Q' carries scale * log2(e)
+            const bool whole = wk.slot < 0;
+            float* dv = whole ? p.dqkv + (size_t)key * (3 * p.D) + 2 * p.D + h * DH : p.part + ((size_t)wk.slot * 2 * TQ + r) * DH;
+            float* dk = whole ? p.dqkv + (size_t)key * (3 * p.D) + p.D + h * DH : p.part + (((size_t)wk.slot * 2 + 1) * TQ + r) * DH;
+            const float kmul = whole ? 1.0f / kLog2e : 1.0f;     // Q' carries scale * log2(e)
 #pragma unroll
             for (int c = 0; c < DH; c += 32) {
                 uint32_t x[32], y[32];
                 tc::tmem_ld32(lane_addr + 128 + c, x);
                 tc::tmem_ld32(lane_addr + 256 + c, y);
                 tc::tmem_ld_wait();
-                if (key < p.S) {
+                if (key < p.S || !whole) {
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
                         *reinterpret_cast<float4*>(dv + c + e) = make_float4(__uint_as_float(x[e]), __uint_as_float(x[e + 1]),
@@ -921,9 +961,38 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
     if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 
+// ---- merging the segments of the split rows -------------------------------------------------------------------------------
+// grid (leftover rows, 128 rows of the resident tile), 128 threads = columns of the head.  Fixed summation order: deterministic.
+__global__ void __launch_bounds__(DH) attn_combine_fwd_kernel(const AttnParams p) {
+    const int row = p.n_full + (int)blockIdx.x, r = (int)blockIdx.y, c = (int)threadIdx.x;
+    const int h = row / p.n_rtiles, q = (row % p.n_rtiles) * TQ + r;
+    const size_t slot0 = (size_t)blockIdx.x * p.segs;
+    float M = -INFINITY;
+    for (int s = 0; s < p.segs; ++s) M = fmaxf(M, __ldg(p.part_ml + ((slot0 + s) * 2 + 0) * TQ + r));
+    float L = 0.0f, o = 0.0f;
+    for (int s = 0; s < p.segs; ++s) {
+        const float w = ex2(__ldg(p.part_ml + ((slot0 + s) * 2 + 0) * TQ + r) - M);
+        L += w * __ldg(p.part_ml + ((slot0 + s) * 2 + 1) * TQ + r);
+        o += w * __ldg(p.part + ((slot0 + s) * 2 * TQ + r) * DH + c);
+    }
+    if (q < p.S) p.ctx_out[(size_t)q * p.D + h * DH + c] = o / L;
+    if (c == 0) p.lse2[(size_t)h * p.S_pad + q] = (q < p.S) ? M + log2f(L) : INFINITY;
+}
+// dst[q, col0 + h*128 + c] = mul * sum over segments of accumulator `arr`
+__global__ void __launch_bounds__(DH) attn_combine_sum_kernel(const AttnParams p, int arr, int col0, float mul) {
+    const int row = p.n_full + (int)blockIdx.x, r = (int)blockIdx.y, c = (int)threadIdx.x;
+    const int h = row / p.n_rtiles, q = (row % p.n_rtiles) * TQ + r;
+    if (q >= p.S) return;
+    const size_t slot0 = (size_t)blockIdx.x * p.segs;
+    float o = 0.0f;
+    for (int s = 0; s < p.segs; ++s) o += __ldg(p.part + (((slot0 + s) * 2 + arr) * TQ + r) * DH + c);
+    p.dqkv[(size_t)q * (3 * p.D) + col0 + h * DH + c] = o * mul;
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
+constexpr int kMaxSlots = 148;      // one segment CTA per SM at most
 struct AttnLayout {
-    size_t planes_off, lse_off, delta_off, total;
+    size_t planes_off, lse_off, delta_off, part_off, ml_off, total;
     int S_pad;
 };
 AttnLayout attn_layout(int64_t S, int64_t heads) {
@@ -933,8 +1002,30 @@ AttnLayout attn_layout(int64_t S, int64_t heads) {
     const size_t planes = (size_t)4 * 2 * heads * l.S_pad * DH * sizeof(__nv_bfloat16);
     l.lse_off = l.planes_off + planes;
     l.delta_off = l.lse_off + (size_t)heads * l.S_pad * sizeof(float);
-    l.total = l.delta_off + (size_t)heads * l.S_pad * sizeof(float);
+    l.part_off = (l.delta_off + (size_t)heads * l.S_pad * sizeof(float) + 255) & ~(size_t)255;
+    l.ml_off = l.part_off + (size_t)kMaxSlots * 2 * TQ * DH * sizeof(float);
+    l.total = l.ml_off + (size_t)kMaxSlots * 2 * TQ * sizeof(float);
     return l;
+}
+// Every CTA needs a whole SM (tiles + all of tensor memory), and a (resident tile, head) row costs the same everywhere, so
+// R rows on n SMs take ceil(R / n) rounds: config 3 has R = 150 rows for 148 SMs -- two rounds, the second one for 2 rows.
+// Rows beyond the last full round are therefore cut into floor(n / leftover) segments of consecutive streamed tiles each
+// (150 rows: 148 whole rows + 2 x 74 segments of 2-3 tiles, 1.03 rounds), whose partial results the combine kernels merge.
+void plan_split(AttnParams& p, int n_tiles) {
+    int nsm = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+    if (const char* e = getenv("OPN_ATTN_SMS")) {      // tests: exercise whole rows + segments at small S
+        const int v = atoi(e);
+        if (v > 0) nsm = v;
+    }
+    if (nsm > kMaxSlots) nsm = kMaxSlots;
+    const int R = p.n_rtiles * p.heads;
+    p.n_full = R / nsm * nsm;
+    const int left = R - p.n_full;
+    p.segs = left > 0 ? nsm / left : 0;
+    if (p.segs > n_tiles) p.segs = n_tiles;
+    if (p.segs < 2) p.n_full = R, p.segs = 0;
+    p.grid = p.n_full + (R - p.n_full) * p.segs;
 }
 constexpr size_t kFwdSmem = 1024 + 3 * 2 * STR_TILE;                        // 3 x (K, V) stages (Q' lives in tensor memory)
 constexpr size_t kBwdSmem = 1024 + 2 * RES_TILE + 3 * STR_TILE;             // two resident tiles + 2 + 1 streamed tiles
@@ -952,13 +1043,33 @@ int fill_params(AttnParams& p, const AttnLayout& l, int64_t S, int64_t D, int64_
     p.seed = seed, p.offset = offset;
     p.planes = reinterpret_cast<const __nv_bfloat16*>(ws + l.planes_off);
     p.ctx = nullptr, p.ctx_out = nullptr, p.dctx = nullptr, p.dqkv = nullptr;
+    p.part = reinterpret_cast<float*>(ws + l.part_off);
+    p.part_ml = reinterpret_cast<float*>(ws + l.ml_off);
+    p.n_rtiles = l.S_pad / TQ;
+    plan_split(p, (int)((S + TK - 1) / TK));
     return OPN_OK;
 }
 
 template <typename Kernel>
 int launch_attn(Kernel kernel, int threads, size_t smem, const CUtensorMap& m128, const CUtensorMap& m64, const AttnParams& p, cudaStream_t s) {
     OPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<dim3((unsigned)(p.S_pad / TQ), (unsigned)p.heads), threads, smem, s>>>(m128, m64, p);
+    kernel<<<dim3((unsigned)p.grid), threads, smem, s>>>(m128, m64, p);
+    OPN_CUDA(cudaGetLastError());
+    count_launch();
+    return OPN_OK;
+}
+int combine_fwd(const AttnParams& p, cudaStream_t s) {
+    const int left = p.n_rtiles * p.heads - p.n_full;
+    if (left <= 0) return OPN_OK;
+    attn_combine_fwd_kernel<<<dim3((unsigned)left, TQ), DH, 0, s>>>(p);
+    OPN_CUDA(cudaGetLastError());
+    count_launch();
+    return OPN_OK;
+}
+int combine_sum(const AttnParams& p, int arr, int col0, float mul, cudaStream_t s) {
+    const int left = p.n_rtiles * p.heads - p.n_full;
+    if (left <= 0) return OPN_OK;
+    attn_combine_sum_kernel<<<dim3((unsigned)left, TQ), DH, 0, s>>>(p, arr, col0, mul);
     OPN_CUDA(cudaGetLastError());
     count_launch();
     return OPN_OK;
@@ -1013,8 +1124,10 @@ extern "C" int opn_attention_fwd(int64_t S, int64_t D, int64_t nhead, const floa
     p.ctx_out = ctx_out;
     const bool single = current_precision() == OPN_PRECISION_16BIT, drop = p_drop > 0.0f;
     const int th = AT + 32 * rng_warps(drop, true);
-    if (single) return drop ? launch_attn(attn_fwd_kernel<1, true>, th, kFwdSmem, m128, m64, p, s) : launch_attn(attn_fwd_kernel<1, false>, th, kFwdSmem, m128, m64, p, s);
-    return drop ? launch_attn(attn_fwd_kernel<3, true>, th, kFwdSmem, m128, m64, p, s) : launch_attn(attn_fwd_kernel<3, false>, th, kFwdSmem, m128, m64, p, s);
+    if (single) rc = drop ? launch_attn(attn_fwd_kernel<1, true>, th, kFwdSmem, m128, m64, p, s) : launch_attn(attn_fwd_kernel<1, false>, th, kFwdSmem, m128, m64, p, s);
+    else rc = drop ? launch_attn(attn_fwd_kernel<3, true>, th, kFwdSmem, m128, m64, p, s) : launch_attn(attn_fwd_kernel<3, false>, th, kFwdSmem, m128, m64, p, s);
+    if (rc != OPN_OK) return rc;
+    return combine_fwd(p, s);
 }
 
 extern "C" int opn_attention_bwd(int64_t S, int64_t D, int64_t nhead, const float* ctx, const float* dctx, float* dqkv, void* workspace,
@@ -1044,6 +1157,9 @@ extern "C" int opn_attention_bwd(int64_t S, int64_t D, int64_t nhead, const floa
     (single ? (drop ? launch_attn(K<1, true>, th, kBwdSmem, m128, m64, p, s) : launch_attn(K<1, false>, th, kBwdSmem, m128, m64, p, s)) \
             : (drop ? launch_attn(K<3, true>, th, kBwdSmem, m128, m64, p, s) : launch_attn(K<3, false>, th, kBwdSmem, m128, m64, p, s)))
     if ((rc = OPN_ATTN_BWD(attn_bwd_q_kernel)) != OPN_OK) return rc;      // writes delta, read by the key-tile kernel
-    return OPN_ATTN_BWD(attn_bwd_kv_kernel);
+    if ((rc = combine_sum(p, 0, 0, p.scale, s)) != OPN_OK) return rc;
+    if ((rc = OPN_ATTN_BWD(attn_bwd_kv_kernel)) != OPN_OK) return rc;
+    if ((rc = combine_sum(p, 0, (int)(2 * D), 1.0f, s)) != OPN_OK) return rc;      // dV
+    return combine_sum(p, 1, (int)D, 1.0f / kLog2e, s);                            // dK (Q' carries scale * log2(e))
 #undef OPN_ATTN_BWD
 }

@@ -475,6 +475,40 @@ def test_fused_attention_head_dim_128(cuda_device, S, nhead, p_drop):
     assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4 * max(1.0, qr.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("S,nhead,sms", [(600, 2, 3), (1000, 1, 7), (333, 1, 2), (130, 2, 3)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_fused_attention_split_rows(cuda_device, monkeypatch, S, nhead, sms, p_drop):
+    """The work split of the fused kernels: with more (resident tile, head) rows than SMs the rows of the last, partial
+    round are cut into segments whose partial results are merged (config 3: 150 rows on 148 SMs).  OPN_ATTN_SMS pretends
+    a small SM count so that whole rows AND segments occur at sizes fp64 math handles; the result must not depend on it."""
+    from oracle import dropout_mask
+    D, d = 128 * nhead, 128
+    seed, offset = 99, 5
+    qkv, dctx = _rand((S, 3 * D), 181 + S), _rand((S, D), 182 + S)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = [z.reshape(S, nhead, d).permute(1, 0, 2) for z in (qr[:, :D], qr[:, D:2 * D], qr[:, 2 * D:])]
+    probs = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    if p_drop > 0:
+        blocks = (S * S + 3) // 4
+        keep = torch.stack([torch.from_numpy(dropout_mask.keep_mask(S * S, p_drop, seed, offset + h * blocks)).reshape(S, S)
+                            for h in range(nhead)])
+        probs = probs * keep.double() / (1.0 - p_drop)
+    ref = (probs @ v).permute(1, 0, 2).reshape(S, D)
+    ref.backward(dctx.double())
+    results = []
+    for env in (str(sms), "148"):
+        monkeypatch.setenv("OPN_ATTN_SMS", env)
+        qg = qkv.to(cuda_device).requires_grad_(True)
+        out = ops.self_attention(qg, nhead, p_drop, seed, offset)
+        out.backward(dctx.to(cuda_device))
+        assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 1e-5
+        assert (qg.grad.cpu().double() - qr.grad).abs().max().item() <= 1e-4 * max(1.0, qr.grad.abs().max().item())
+        results.append((out.detach().cpu(), qg.grad.cpu()))
+    # the two schedules agree far inside the tolerance (different summation order only)
+    assert (results[0][0] - results[1][0]).abs().max().item() <= 2e-6
+    assert (results[0][1] - results[1][1]).abs().max().item() <= 2e-5 * max(1.0, qr.grad.abs().max().item())
+
+
 # ---- dropout (train mode of the encoder layer) ------------------------------------------------
 @pytest.mark.parametrize("n,p,seed,offset", [(1, 0.1, 1, 0), (4, 0.1, 7, 3), (1027, 0.1, 1234, 0), (65536, 0.5, 2 ** 40 + 5, 2 ** 33),
                                               (100003, 0.0, 9, 11), (300 * 300 + 1, 0.9, 3, 12345)])
