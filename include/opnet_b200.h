@@ -172,6 +172,27 @@ OPN_API int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1, int64_t H2, const fl
                   const float* cells1, const float* gates2, const float* cells2, const float* d_hs2, float* d_gates1,
                   float* d_gates2, float* d_logits, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- LSTM weight gradients -------------------------------------------------------------
+ * The time-parallel contractions autograd forms for the weights of nn.LSTM (baselines/learned_models.py:39,46,76,113,
+ * 146,192), several per launch, straight from the fp32 tensors on tcgen05 (opn_wgrad_tc.cu): no operand pre-pass, no zero
+ * fill, no atomics (the partial sums of the row ranges are added in a fixed order).  One job:
+ *   out[M, N] (ldc) = sum over rows r of a[r, 0..M)^T b[r - shift, 0..N)
+ *   a [rows, M] (lda) = d(gates), M = 4H a multiple of 128;  b [rows, N] (ldb) = the layer input (shift 0: dW_ih) or its
+ *   hidden states (shift 1: dW_hh; rows with r % T == 0, the first frame of every video, take no part).
+ * Arithmetic as opn_sgemm's tensor-core path: bf16 hi + lo operands, three products (one in OPN_PRECISION_16BIT).
+ * workspace: opn_wgrad_workspace_bytes(n_jobs, jobs) bytes (status words as for opn_lstm_status, partial sums);
+ * the job array is a HOST array read during the call. */
+typedef struct {
+    const float* a;
+    const float* b;
+    float* out;
+    int64_t lda, ldb, ldc;
+    int64_t rows, T, M, N;
+    int32_t shift;
+} opn_wgrad_job;
+OPN_API int64_t opn_wgrad_workspace_bytes(int32_t n_jobs, const opn_wgrad_job* jobs);
+OPN_API int opn_wgrad(int32_t n_jobs, const opn_wgrad_job* jobs, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- fused self-attention (transformer_lstm encoder) -----------------------------------
  * softmax(Q K^T / sqrt(d)) V per head over ONE sequence of S rows, as nn.MultiheadAttention computes it inside
  * nn.TransformerEncoderLayer (baselines/learned_models.py:166-168,184; the sequence axis of the reference is B*T).

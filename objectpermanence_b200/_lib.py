@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_ulonglong, c_void_p, POINTER
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # OPN_B200_LIB selects a development variant of the library (e.g. the phase-counter build); never a fallback
@@ -18,6 +18,14 @@ OPN_ERR_TIMEOUT = -4
 
 # name -> (restype, argtypes); mirrors include/opnet_b200.h one to one
 _P = c_void_p
+
+
+class WgradJob(ctypes.Structure):
+    """opn_wgrad_job of include/opnet_b200.h."""
+    _fields_ = [("a", c_void_p), ("b", c_void_p), ("out", c_void_p), ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64),
+                ("rows", c_int64), ("T", c_int64), ("M", c_int64), ("N", c_int64), ("shift", c_int32)]
+
+
 SIGNATURES = {
     "opn_version": (c_int, []),
     "opn_last_error": (c_char_p, []),
@@ -38,6 +46,8 @@ SIGNATURES = {
     "opn_opnet_fwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 16 + [c_int64, _P]),
     "opn_opnet_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "opn_opnet_bwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 15 + [c_int64, _P]),
+    "opn_wgrad_workspace_bytes": (c_int64, [c_int32, POINTER(WgradJob)]),
+    "opn_wgrad": (c_int, [c_int32, POINTER(WgradJob), _P, c_int64, _P]),
     "opn_attention_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "opn_attention_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, _P]),
     "opn_attention_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_float, c_uint64, c_uint64, _P]),

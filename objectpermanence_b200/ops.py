@@ -359,10 +359,55 @@ def _lstm_recurrence_backward(w_hh, gates, cells, dhs):
     return dgates
 
 
+def wgrad_jobs_run(jobs) -> None:
+    """One launch of opn_wgrad over `jobs` = [(a [rows, M], b [rows, N], out [M, N], T, shift), ...]: out = sum_r a[r]^T
+    b[r - shift] (shift 1: rows with r % T == 0 excluded).  The tcgen05 weight-gradient kernel of csrc/opn_wgrad_tc.cu."""
+    lib = _lib.load()
+    arr = (_lib.WgradJob * len(jobs))()
+    for j, (a, b, out, T, shift) in enumerate(jobs):
+        rows, M = a.shape
+        N = b.shape[1]
+        assert b.shape[0] == rows and out.shape == (M, N) and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+        arr[j] = _lib.WgradJob(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.stride(0), b.stride(0), out.stride(0), rows, T, M, N,
+                               int(shift))
+    n = lib.opn_wgrad_workspace_bytes(len(jobs), arr)
+    if n <= 0:
+        _lib.check(-1, "opn_wgrad_workspace_bytes")
+    ws = torch.empty(n, dtype=torch.uint8, device=jobs[0][0].device)
+    rc = lib.opn_wgrad(len(jobs), arr, ws.data_ptr(), n, _stream())
+    _lib.check(rc, "opn_wgrad")
+    _lstm_check(jobs[0][0].device, "opn_wgrad")
+
+
+def wgrad_tc_wanted(rows: int, M: int) -> bool:
+    """The tcgen05 weight-gradient kernel takes the LSTM weight gradients from 1024 rows on (below that the exact-fp32
+    FFMA contraction of opn_sgemm is as fast); OPN_WGRAD=sgemm keeps the general path (A/B runs, tests)."""
+    return rows >= 1024 and M % 128 == 0 and os.environ.get("OPN_WGRAD", "tc") != "sgemm"
+
+
+def _lstm_wgrad_jobs(dgates, x, hs, w_ih, w_hh, need_dw_ih, need_dw_hh):
+    """-> (jobs for wgrad_jobs_run, dW_ih, dW_hh) of one LSTM layer."""
+    B, T, I = x.shape
+    H = w_hh.shape[1]
+    jobs, dw_ih, dw_hh = [], None, None
+    dg = dgates.reshape(B * T, 4 * H)
+    if need_dw_ih:
+        dw_ih = _grad_like(w_ih)
+        jobs.append((dg, x.reshape(B * T, I), dw_ih, T, 0))
+    if need_dw_hh:
+        dw_hh = _grad_like(w_hh)
+        jobs.append((dg, hs.reshape(B * T, H), dw_hh, T, 1))
+    return jobs, dw_ih, dw_hh
+
+
 def _lstm_weight_grads(dgates, x, hs, w_ih, w_hh, need_dw_ih, need_dw_hh):
     """The two time-parallel weight-gradient contractions of one LSTM layer -> (dW_ih, dW_hh)."""
     B, T, I = x.shape
     H = w_hh.shape[1]
+    if wgrad_tc_wanted(B * T, 4 * H) and (need_dw_ih or need_dw_hh):
+        jobs, dw_ih, dw_hh = _lstm_wgrad_jobs(dgates.contiguous(), x.contiguous(), hs.contiguous(), w_ih, w_hh, need_dw_ih, need_dw_hh)
+        wgrad_jobs_run(jobs)
+        return dw_ih, dw_hh
     dw_ih = dw_hh = None
     if need_dw_ih:
         dw_ih = _grad_like(w_ih)
@@ -550,6 +595,14 @@ class OPNetTrunkFn(torch.autograd.Function):
             _lib.check(rc, "opn_opnet_bwd")
             _lstm_check(dev, "opn_opnet_bwd")
             x1 = boxes.reshape(B, T, -1)
+            if wgrad_tc_wanted(B * T, 4 * H1) and all(need[1:6]):
+                # all five weight gradients as ONE launch of the tcgen05 weight-gradient kernel (+ its reduction);
+                # dW_pred in the transposed orientation (H1 = the 128-wide dimension)
+                j2, dw_ih2, dw_hh2 = _lstm_wgrad_jobs(dgates2, fb, hs2, w_ih2, w_hh2, True, True)
+                j1, dw_ih1, dw_hh1 = _lstm_wgrad_jobs(dgates1, x1, hs1, w_ih1, w_hh1, True, True)
+                dw_pred_t = torch.empty(H1, 15, device=dev, dtype=torch.float32)
+                wgrad_jobs_run(j2 + j1 + [(hs1.reshape(B * T, H1), dl.reshape(B * T, 15), dw_pred_t, T, 0)])
+                return None, dw_ih1, dw_hh1, dw_pred_t.t(), dw_ih2, dw_hh2, None
             if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "1") not in ("0", "") and all(need[1:6]):
                 # The five weight-gradient contractions are independent of each other and none fills the GPU (pre-pass,
                 # 16-64 output tiles, split-K): LSTM2's stay on the main stream, LSTM1's and dW_pred run beside them

@@ -509,6 +509,36 @@ def test_fused_attention_split_rows(cuda_device, monkeypatch, S, nhead, sms, p_d
     assert (results[0][1] - results[1][1]).abs().max().item() <= 2e-5 * max(1.0, qr.grad.abs().max().item())
 
 
+@pytest.mark.parametrize("B,T,M,N,shift", [(1, 64, 128, 64, 0), (3, 50, 128, 6, 0), (2, 100, 256, 90, 0), (5, 37, 256, 256, 1),
+                                            (4, 300, 1024, 256, 1), (7, 33, 2048, 512, 1), (2, 70, 512, 300, 1), (1, 1, 128, 15, 1)])
+@pytest.mark.parametrize("mode", ["fp32", "16bit"])
+def test_wgrad_tc_kernel(cuda_device, B, T, M, N, shift, mode):
+    """The tcgen05 weight-gradient kernel (csrc/opn_wgrad_tc.cu) against fp64: ragged row counts (tail k-block), N below /
+    across / above the 64- and 256-column blocks, unaligned rows of b (N = 6, 15, 90), the one-row shift with the first
+    frame of every video excluded (dW_hh), several jobs in one launch."""
+    rows = B * T
+    a, b = _rand((rows, M), 300 + rows), _rand((rows, N), 301 + rows)
+    a2 = _rand((rows, M), 302 + rows)
+    bs = b.double()
+    if shift:
+        bs = torch.roll(bs, 1, dims=0)
+        bs[::T] = 0.0      # rows r with r % T == 0 meet nothing
+    want, want2 = a.double().t() @ bs, a2.double().t() @ b.double()
+    ad, bd, a2d = a.to(cuda_device), b.to(cuda_device), a2.to(cuda_device)
+    out = torch.full((M, N), float("nan"), device=cuda_device)
+    out2 = torch.full((M, N + 3), float("nan"), device=cuda_device)      # a strided destination
+    ops.set_precision(mode)
+    try:
+        ops.wgrad_jobs_run([(ad, bd, out, T, shift), (a2d, bd, out2[:, :N], T, 0)])
+    finally:
+        ops.set_precision("fp32")
+    torch.cuda.synchronize()
+    tol = (3e-5 if mode == "fp32" else 1e-2) * max(1.0, want.abs().max().item())
+    assert (out.cpu().double() - want).abs().max().item() <= tol
+    assert (out2[:, :N].cpu().double() - want2).abs().max().item() <= tol
+    assert torch.isnan(out2[:, N:]).all()      # nothing written outside the N columns
+
+
 # ---- dropout (train mode of the encoder layer) ------------------------------------------------
 @pytest.mark.parametrize("n,p,seed,offset", [(1, 0.1, 1, 0), (4, 0.1, 7, 3), (1027, 0.1, 1234, 0), (65536, 0.5, 2 ** 40 + 5, 2 ** 33),
                                               (100003, 0.0, 9, 11), (300 * 300 + 1, 0.9, 3, 12345)])
