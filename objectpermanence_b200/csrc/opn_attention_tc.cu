@@ -359,6 +359,8 @@ struct Shared {
 // warps one tile ahead and handed over through shared memory, so that they fill the issue slots the latency-bound softmax
 // warps leave idle instead of doubling their work (forward 0.56 -> 1.05 ms with the mask generated in line).
 constexpr int rng_warps(bool drop, bool fwd) { return drop ? (fwd ? 4 : 2) : 0; }
+// the query-tile backward has the registers for four generator warps (168 per thread), the key-tile one (234) has not
+constexpr int rng_warps_q(bool drop) { return drop ? 4 : 0; }
 
 // ======================================================= forward =======================================================
 // TMEM: S tiles 0-63 / 64-127 (double buffered), O 128-255 (accumulated over all key tiles), P planes 256-319 / 320-383,
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
 // TMEM: (S, dP) pairs 0-127 / 128-255 (double buffered), dQ 256-383, dS planes 384-447 / 448-511.
 // Shared memory: Q', dO resident; K double buffered (read by the score product and, a phase later, by dQ += dS K), V single.
 template <int PASSES, bool DROP>
-__global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_q_kernel(const __grid_constant__ CUtensorMap map128,
+__global__ void __launch_bounds__(AT + 32 * rng_warps_q(DROP), 1) attn_bwd_q_kernel(const __grid_constant__ CUtensorMap map128,
                                                            const __grid_constant__ CUtensorMap map64, const AttnParams p) {
     constexpr int PL = PASSES == 3 ? 2 : 1;
     extern __shared__ unsigned char smem_raw[];
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
             mbar_init(&sh.s_empty[i], 4);
             mbar_init(&sh.p_full[i], 4);
             mbar_init(&sh.pv_full[i], 1);
-            mbar_init(&sh.rng_full[i], rng_warps(true, false));
+            mbar_init(&sh.rng_full[i], rng_warps_q(true));
             mbar_init(&sh.rng_empty[i], 4);
         }
         mbar_fence_init();
@@ -627,17 +629,13 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
     volatile int* abort_s = &sh.abort_flag;
 
     if (warp >= 6) {
-        // ---- mask generators (train mode only): two rows per thread, one tile ahead ---------------------------------------
+        // ---- mask generators (train mode only): one row per thread, one tile ahead -----------------------------------------
         const unsigned long long drop_off = p.offset + (unsigned long long)h * (((unsigned long long)p.S * p.S + 3ull) >> 2);
         for (int j = 0; j < n_tiles; ++j) {
-            unsigned long long bits[2];
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-                bits[half] = keep_bits_row((unsigned long long)(qt * TQ + (warp - 6) * 32 + lane + 64 * half) * p.S + (unsigned long long)(j0 + j) * TK,
-                                           p.seed, drop_off, p.drop_threshold);
+            const unsigned long long bits = keep_bits_row((unsigned long long)(qt * TQ + (warp - 6) * 32 + lane) * p.S + (unsigned long long)(j0 + j) * TK,
+                                                          p.seed, drop_off, p.drop_threshold);
             if (j >= 1 && !await(&sh.rng_empty[0], (uint32_t)(j - 1) & 1u, p.status, abort_s)) break;     // tile j-1's bits have been read
-            keep_bits[(warp - 6) * 32 + lane] = bits[0];
-            keep_bits[(warp - 6) * 32 + lane + 64] = bits[1];
+            keep_bits[(warp - 6) * 32 + lane] = bits;
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh.rng_full[0]);
         }
@@ -852,24 +850,43 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            bool ok = await(&sh.res_full, 0, p.status, abort_s);
+            // Order per query tile i:  dP^T(i) | S^T(i+1) | dV(i), dK(i).  S^T of the NEXT tile is queued as soon as the
+            // softmax threads hold S^T(i) and dP^T(i) in registers, so the tensor core works through it while they form
+            // P^T / dS^T of tile i (the serial order S^T, dP^T -> softmax -> dV, dK left it idle 2,500 of 7,200 clocks per
+            // tile).  dP^T(i+1) has to wait for the single dO buffer, i.e. for dV(i).
+            bool ok = await(&sh.res_full, 0, p.status, abort_s) && await(&sh.str_full[0], 0, p.status, abort_s);
+            if (ok) {
+                tc::fence_after();
+                issue_score<PASSES>(tmem, k_s, qd_s);     // S^T(0) = K Q'^T
+            }
+            APH_DECL
             for (int i = 0; i < n_tiles && ok; ++i) {
                 const int st = i & 1;
-                ok = await(&sh.str_full[st], (uint32_t)(i >> 1) & 1u, p.status, abort_s) && await(&sh.v_full, (uint32_t)i & 1u, p.status, abort_s);
-                if (ok && i >= 1) ok = await(&sh.s_empty[0], (uint32_t)(i - 1) & 1u, p.status, abort_s);
-                if (!ok) break;
+                if (!await(&sh.v_full, (uint32_t)i & 1u, p.status, abort_s)) break;
+                APH(0);
                 tc::fence_after();
-                issue_score<PASSES>(tmem, k_s, qd_s + st * STR_TILE);     // S^T  = K Q'^T
-                issue_score<PASSES>(tmem + TK, v_s, do_s);                // dP^T = V dO^T
-                tc::umma_commit(&sh.s_full[0]);
+                issue_score<PASSES>(tmem + TK, v_s, do_s);                // dP^T(i) = V dO^T
+                tc::umma_commit(&sh.s_full[0]);                          // ... and S^T(i), issued earlier
+                APH(1);
+                if (i + 1 < n_tiles) {
+                    ok = await(&sh.str_full[st ^ 1], (uint32_t)((i + 1) >> 1) & 1u, p.status, abort_s) &&
+                         await(&sh.s_empty[0], (uint32_t)i & 1u, p.status, abort_s);      // S^T(i), dP^T(i) are in registers
+                    if (!ok) break;
+                    tc::fence_after();
+                    issue_score<PASSES>(tmem, k_s, qd_s + (st ^ 1) * STR_TILE);     // S^T(i+1)
+                }
+                APH(2);
                 if (!await(&sh.p_full[0], (uint32_t)i & 1u, p.status, abort_s)) break;           // P^T and dS^T planes written
+                APH(3);
                 tc::fence_after();
                 issue_second<PASSES>(tmem + 128, tmem + 384, do_s, i > 0);                       // dV += P^T dO
                 tc::umma_commit(&sh.v_empty);
                 issue_second<PASSES>(tmem + 256, tmem + 448, qd_s + st * STR_TILE, i > 0);       // dK += dS^T Q'
                 tc::umma_commit(&sh.str_empty[st]);
                 tc::umma_commit(&sh.done);
+                APH(4);
             }
+            APH_STORE(p.status, 3);
         }
     } else {
         const int qd = warp & 3, r = qd * 32 + lane;
@@ -877,6 +894,7 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
         const int et = tid - 64;      // 0..127 among the softmax threads
         const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16);
         bool dead = false;     // never leave the others alone at the named barrier below: keep stepping, the waits return at once
+        APH_DECL
         for (int i = 0; i < n_tiles; ++i) {
             // row statistics of the 64 queries of this tile (the named barriers order fill and use)
             {
@@ -886,7 +904,9 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
                 if (et < 64) lse_s[et] = v; else delta_s[et - 64] = v;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            APH(0);
             if (!dead && !await(&sh.s_full[0], (uint32_t)i & 1u, p.status, abort_s)) dead = true;
+            APH(1);
             tc::fence_after();
             float pt[TK], ds[TK];
             {
@@ -922,14 +942,18 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
                     ds[c] = pv * (dp - delta_s[c]);
                 }
             }
+            APH(2);
             // the planes were last read by the dV / dK products of tile i-1
             if (!dead && i >= 1 && !await(&sh.done, (uint32_t)(i - 1) & 1u, p.status, abort_s)) dead = true;
+            APH(3);
             store_row_tmem<PL>(lane_addr + 384, pt);
             store_row_tmem<PL>(lane_addr + 448, ds);
             tc::fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh.p_full[0]);
+            APH(4);
         }
+        if (tid == 64) APH_STORE(p.status, 2);
         if (!dead && await(&sh.done, (uint32_t)(n_tiles - 1) & 1u, p.status, abort_s)) {
             tc::fence_after();
             const bool whole = wk.slot < 0;
@@ -968,8 +992,10 @@ __global__ void __launch_bounds__(DH) attn_combine_fwd_kernel(const AttnParams p
     const int h = row / p.n_rtiles, q = (row % p.n_rtiles) * TQ + r;
     const size_t slot0 = (size_t)blockIdx.x * p.segs;
     float M = -INFINITY;
+#pragma unroll 8
     for (int s = 0; s < p.segs; ++s) M = fmaxf(M, __ldg(p.part_ml + ((slot0 + s) * 2 + 0) * TQ + r));
     float L = 0.0f, o = 0.0f;
+#pragma unroll 8      // independent loads in flight: the loop is a chain of L2 latencies otherwise (27 us for 74 segments)
     for (int s = 0; s < p.segs; ++s) {
         const float w = ex2(__ldg(p.part_ml + ((slot0 + s) * 2 + 0) * TQ + r) - M);
         L += w * __ldg(p.part_ml + ((slot0 + s) * 2 + 1) * TQ + r);
@@ -985,6 +1011,7 @@ __global__ void __launch_bounds__(DH) attn_combine_sum_kernel(const AttnParams p
     if (q >= p.S) return;
     const size_t slot0 = (size_t)blockIdx.x * p.segs;
     float o = 0.0f;
+#pragma unroll 8
     for (int s = 0; s < p.segs; ++s) o += __ldg(p.part + (((slot0 + s) * 2 + arr) * TQ + r) * DH + c);
     p.dqkv[(size_t)q * (3 * p.D) + col0 + h * DH + c] = o * mul;
 }
@@ -1152,11 +1179,12 @@ extern "C" int opn_attention_bwd(int64_t S, int64_t D, int64_t nhead, const floa
     fill_params(p, l, S, D, nhead, ws, p_drop, seed, offset);
     p.ctx = ctx, p.dctx = dctx, p.dqkv = dqkv;
     const bool single = current_precision() == OPN_PRECISION_16BIT, drop = p_drop > 0.0f;
-    const int th = AT + 32 * rng_warps(drop, false);
+    int th = AT + 32 * rng_warps_q(drop);
 #define OPN_ATTN_BWD(K)                                                                                           \
     (single ? (drop ? launch_attn(K<1, true>, th, kBwdSmem, m128, m64, p, s) : launch_attn(K<1, false>, th, kBwdSmem, m128, m64, p, s)) \
             : (drop ? launch_attn(K<3, true>, th, kBwdSmem, m128, m64, p, s) : launch_attn(K<3, false>, th, kBwdSmem, m128, m64, p, s)))
     if ((rc = OPN_ATTN_BWD(attn_bwd_q_kernel)) != OPN_OK) return rc;      // writes delta, read by the key-tile kernel
+    th = AT + 32 * rng_warps(drop, false);
     if ((rc = combine_sum(p, 0, 0, p.scale, s)) != OPN_OK) return rc;
     if ((rc = OPN_ATTN_BWD(attn_bwd_kv_kernel)) != OPN_OK) return rc;
     if ((rc = combine_sum(p, 0, (int)(2 * D), 1.0f, s)) != OPN_OK) return rc;      // dV

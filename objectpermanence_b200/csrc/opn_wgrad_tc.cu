@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
     for (int j = 0; j < 4; ++j) {
         const int n = n0 + ty + 8 * j;      // < n_pad: n_pad is a multiple of 64
         float acc = 0.0f;
+#pragma unroll 4
         for (int ks = 0; ks < jb.ksplit; ++ks) acc += __ldg(jb.part + ((size_t)ks * jb.n_pad + n) * jb.M + m0 + tx);
         t[ty + 8 * j][tx] = acc;
     }

@@ -265,7 +265,11 @@ class LinearFn(torch.autograd.Function):
             sgemm(dy, weight, dx, trans_a=False, trans_b=False, M=M, N=K, K=N, lda=N, ldb=K, ldc=K)
         if ctx.needs_input_grad[1]:
             dw = _grad_like(weight)
-            sgemm(dy, x, dw, trans_a=True, trans_b=False, M=N, N=K, K=M, lda=N, ldb=K, ldc=K)
+            if wgrad_tc_wanted(M, N) and K >= 64:
+                # dW = dy^T x contracts both operands over their rows, like the LSTM weight gradients: same kernel
+                wgrad_jobs_run([(dy.reshape(M, N), x.reshape(M, K), dw, M, 0)])
+            else:
+                sgemm(dy, x, dw, trans_a=True, trans_b=False, M=N, N=K, K=M, lda=N, ldb=K, ldc=K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(N, device=x.device, dtype=torch.float32)
             _lib.check(_lib.load().opn_colsum(M, N, dy.data_ptr(), N, db.data_ptr(), 0, _stream()), "opn_colsum")

@@ -18,3 +18,15 @@ for role, name, labels in ((0, "softmax thread", ["loop", "wait s_full", "tmem l
                            (1, "MMA thread", ["wait K/V tile", "wait S buffer", "issue S(j+1)", "wait P(j)", "issue PV(j)"])):
     ph = w[32 + 8 * role: 32 + 8 * role + len(labels)].tolist()
     print(f"{name:15s}: total {sum(ph) / n:7.0f} clk/tile | " + "  ".join(f"{l} {v / n:6.0f}" for l, v in zip(labels, ph)))
+
+# ---- backward, key-tile kernel (roles 2, 3) ----
+dctx = torch.rand(S, D, device=dev) * 2 - 1
+dqkv = torch.empty(S, 3 * D, device=dev)
+for _ in range(2):
+    _lib.check(lib.opn_attention_bwd(S, D, nhead, out.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), ws.numel(), 0.0, 0, 0, s))
+torch.cuda.synchronize()
+w = ws[:4096].view(torch.int64).cpu()
+for role, name, labels in ((2, "bwd_kv softmax thread", ["row stats + barriers", "wait S/dP", "tmem ld + exp + dS", "wait planes free", "cvt + tmem st + arrive"]),
+                           (3, "bwd_kv MMA thread", ["wait dO tile", "issue dP^T(i)", "wait + issue S^T(i+1)", "wait planes", "issue dV, dK"])):
+    ph = w[32 + 8 * role: 32 + 8 * role + len(labels)].tolist()
+    print(f"{name:22s}: total {sum(ph) / n:7.0f} clk/tile | " + "  ".join(f"{l} {v / n:6.0f}" for l, v in zip(labels, ph)))
