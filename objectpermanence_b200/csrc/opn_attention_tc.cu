@@ -15,7 +15,10 @@
 // transposed copies.  P / dS never touch shared memory: the softmax threads (thread = tile row = TMEM lane) write them with
 // tcgen05.st into tensor memory, from where the second product reads its A operand.
 // Attention-weight dropout (train mode) uses the mask of opn_dropout: element (q, k) of head h is element q*S + k of
-// the stream (seed, offset + h * ceil(S*S/4)); regenerated in the backward kernels, never stored.
+// the stream (seed, offset + h * ceil(S*S/4)).  The forward kernel generates it (extra warps, one tile ahead) and leaves it
+// as one 64-bit word per (query, 64-key tile) in the workspace (23 MB at S = 9600, 2 heads); the backward kernels load
+// the words (the key-tile kernel transposes them by shuffles) instead of running Philox again: regenerating the mask in
+// both backward kernels had cost 0.40 ms of the 1.45 ms backward pass.
 #include <stdlib.h>
 
 #include <cuda_bf16.h>
@@ -56,6 +59,9 @@ struct AttnParams {
     // work split (see plan_split): CTAs [0, n_full) own a whole row of streamed tiles of one (resident tile, head); every
     // leftover (resident tile, head) is cut into `segs` segments of consecutive streamed tiles, one CTA each, whose partial
     // accumulators go to `part` and are merged by the combine kernels
+    unsigned long long* keep;   // [head][key tile][S_pad]: dropout keep bits of 64 keys per query row, written by the forward
+                                // kernel (train mode) and read by both backward kernels instead of re-running Philox
+    int n_ktiles;
     float* part;             // [slot][2][128][128]
     float* part_ml;          // [slot][2][128]   forward: reference maximum and sum of exponentials of a segment
     int n_rtiles, n_full, segs, grid;
@@ -196,36 +202,6 @@ __device__ __forceinline__ unsigned long long keep_bits_row(unsigned long long i
     }
     return bits;
 }
-// keep bits of the 64 elements (q0 + c) * S + key, c = 0..63, of the dropout stream (bit c), for the 32 consecutive keys of a
-// warp (key & 3 == lane & 3) when S % 4 == 0: the four lanes of a group share one Philox block per query, so each lane
-// generates the blocks of 16 queries and the group exchanges them as nibbles (16 Philox calls per thread instead of 64)
-__device__ __forceinline__ unsigned long long keep_bits_col_shared(unsigned long long q0, int S, int key, int lane, unsigned long long seed,
-                                                                   unsigned long long offset, unsigned int threshold) {
-    const int w = lane & 3;
-    unsigned long long mine = 0ull;
-#pragma unroll 4
-    for (int t = 0; t < 16; ++t) {
-        const unsigned long long q = q0 + (unsigned long long)(4 * t + w);
-        const uint4 r = philox(offset + ((q * (unsigned long long)S + (unsigned long long)key) >> 2), seed);
-        const unsigned long long nib = (unsigned long long)((r.x >= threshold ? 1u : 0u) | (r.y >= threshold ? 2u : 0u) |
-                                                            (r.z >= threshold ? 4u : 0u) | (r.w >= threshold ? 8u : 0u));
-        mine |= nib << (4 * t);
-    }
-    unsigned long long bits = 0ull;
-#pragma unroll
-    for (int src = 0; src < 4; ++src) {
-        const unsigned long long v = __shfl_sync(0xffffffffu, mine, (lane & ~3) | src);
-#pragma unroll
-        for (int t = 0; t < 16; ++t) bits |= ((v >> (4 * t + w)) & 1ull) << (4 * t + src);
-    }
-    return bits;
-}
-__device__ __forceinline__ bool keep_one(unsigned long long i, unsigned long long seed, unsigned long long offset, unsigned int threshold) {
-    const uint4 r = philox(offset + (i >> 2), seed);
-    const unsigned int w[4] = {r.x, r.y, r.z, r.w};
-    return w[i & 3] >= threshold;
-}
-
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -413,8 +389,10 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, true), 1) attn_fwd_k
         for (int j = 0; j < n_tiles; ++j) {
             const int b = j & 1;
             if (j >= 2 && !await(&sh.rng_empty[b], ((uint32_t)(j >> 1) - 1u) & 1u, p.status, abort_s)) break;
-            keep_bits[b][r] = keep_bits_row((unsigned long long)(qt * TQ + r) * p.S + (unsigned long long)(j0 + j) * TK, p.seed, drop_off,
-                                            p.drop_threshold);
+            const unsigned long long bits = keep_bits_row((unsigned long long)(qt * TQ + r) * p.S + (unsigned long long)(j0 + j) * TK, p.seed,
+                                                          drop_off, p.drop_threshold);
+            keep_bits[b][r] = bits;
+            p.keep[((size_t)h * p.n_ktiles + (j0 + j)) * p.S_pad + qt * TQ + r] = bits;      // for the backward kernels
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh.rng_full[b]);
         }
@@ -629,11 +607,9 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps_q(DROP), 1) attn_bwd_q_ker
     volatile int* abort_s = &sh.abort_flag;
 
     if (warp >= 6) {
-        // ---- mask generators (train mode only): one row per thread, one tile ahead -----------------------------------------
-        const unsigned long long drop_off = p.offset + (unsigned long long)h * (((unsigned long long)p.S * p.S + 3ull) >> 2);
+        // ---- mask loaders (train mode only): the keep bits the forward kernel left, one row per thread, one tile ahead -------
         for (int j = 0; j < n_tiles; ++j) {
-            const unsigned long long bits = keep_bits_row((unsigned long long)(qt * TQ + (warp - 6) * 32 + lane) * p.S + (unsigned long long)(j0 + j) * TK,
-                                                          p.seed, drop_off, p.drop_threshold);
+            const unsigned long long bits = __ldcs(p.keep + ((size_t)h * p.n_ktiles + (j0 + j)) * p.S_pad + qt * TQ + (warp - 6) * 32 + lane);
             if (j >= 1 && !await(&sh.rng_empty[0], (uint32_t)(j - 1) & 1u, p.status, abort_s)) break;     // tile j-1's bits have been read
             keep_bits[(warp - 6) * 32 + lane] = bits;
             __syncwarp();
@@ -810,20 +786,25 @@ __global__ void __launch_bounds__(AT + 32 * rng_warps(DROP, false), 1) attn_bwd_
     volatile int* abort_s = &sh.abort_flag;
 
     if (warp >= 6) {
-        // ---- mask generators (train mode only): the bits of (query i*64 + c, key) for two key rows per thread ---------------
-        const unsigned long long drop_off = p.offset + (unsigned long long)h * (((unsigned long long)p.S * p.S + 3ull) >> 2);
-        const bool shared_blocks = (p.S & 3) == 0;
+        // ---- mask loaders (train mode only): the forward kernel left one word per (query, 64-key tile); this CTA needs, per key
+        // row, the bits of the 64 queries of the tile: a 64 x 64 bit transpose per half of the resident tile, by shuffles
+        // (a lane holds the words of queries lane and lane + 32).  Two key rows per thread: lt and lt + 64.
+        const int lt = (warp - 6) * 32 + lane;
         for (int i = 0; i < n_tiles; ++i) {
             unsigned long long out[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int key = kt * TQ + (warp - 6) * 32 + lane + 64 * half;
+                unsigned long long wa = 0ull, wb = 0ull;
+                if (kt * 2 + half < p.n_ktiles) {
+                    const unsigned long long* src = p.keep + ((size_t)h * p.n_ktiles + (kt * 2 + half)) * p.S_pad + (size_t)(i0 + i) * TK;
+                    wa = __ldcs(src + lane), wb = __ldcs(src + lane + 32);
+                }
                 unsigned long long bits = 0ull;
-                if (shared_blocks) {
-                    bits = keep_bits_col_shared((unsigned long long)(i0 + i) * TK, p.S, key, lane, p.seed, drop_off, p.drop_threshold);
-                } else {
-                    for (int c = 0; c < TK; ++c)
-                        if (keep_one((unsigned long long)((i0 + i) * TK + c) * p.S + (unsigned long long)key, p.seed, drop_off, p.drop_threshold)) bits |= 1ull << c;
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    const unsigned long long x = __shfl_sync(0xffffffffu, wa, c), y = __shfl_sync(0xffffffffu, wb, c);
+                    bits |= ((x >> lt) & 1ull) << c;
+                    bits |= ((y >> lt) & 1ull) << (c + 32);
                 }
                 out[half] = bits;
             }
@@ -1019,7 +1000,7 @@ __global__ void __launch_bounds__(DH) attn_combine_sum_kernel(const AttnParams p
 // ---- host side ------------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 148;      // one segment CTA per SM at most
 struct AttnLayout {
-    size_t planes_off, lse_off, delta_off, part_off, ml_off, total;
+    size_t planes_off, lse_off, delta_off, part_off, ml_off, keep_off, total;
     int S_pad;
 };
 AttnLayout attn_layout(int64_t S, int64_t heads) {
@@ -1031,7 +1012,8 @@ AttnLayout attn_layout(int64_t S, int64_t heads) {
     l.delta_off = l.lse_off + (size_t)heads * l.S_pad * sizeof(float);
     l.part_off = (l.delta_off + (size_t)heads * l.S_pad * sizeof(float) + 255) & ~(size_t)255;
     l.ml_off = l.part_off + (size_t)kMaxSlots * 2 * TQ * DH * sizeof(float);
-    l.total = l.ml_off + (size_t)kMaxSlots * 2 * TQ * sizeof(float);
+    l.keep_off = l.ml_off + (size_t)kMaxSlots * 2 * TQ * sizeof(float);
+    l.total = l.keep_off + (size_t)heads * ((S + TK - 1) / TK) * l.S_pad * sizeof(unsigned long long);
     return l;
 }
 // Every CTA needs a whole SM (tiles + all of tensor memory), and a (resident tile, head) row costs the same everywhere, so
@@ -1072,6 +1054,8 @@ int fill_params(AttnParams& p, const AttnLayout& l, int64_t S, int64_t D, int64_
     p.ctx = nullptr, p.ctx_out = nullptr, p.dctx = nullptr, p.dqkv = nullptr;
     p.part = reinterpret_cast<float*>(ws + l.part_off);
     p.part_ml = reinterpret_cast<float*>(ws + l.ml_off);
+    p.keep = reinterpret_cast<unsigned long long*>(ws + l.keep_off);
+    p.n_ktiles = (int)((S + TK - 1) / TK);
     p.n_rtiles = l.S_pad / TQ;
     plan_split(p, (int)((S + TK - 1) / TK));
     return OPN_OK;
