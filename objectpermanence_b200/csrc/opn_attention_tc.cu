@@ -972,15 +972,33 @@ __global__ void __launch_bounds__(DH) attn_combine_fwd_kernel(const AttnParams p
     const int row = p.n_full + (int)blockIdx.x, r = (int)blockIdx.y, c = (int)threadIdx.x;
     const int h = row / p.n_rtiles, q = (row % p.n_rtiles) * TQ + r;
     const size_t slot0 = (size_t)blockIdx.x * p.segs;
+    // batches of 8 segments with all their loads in flight (a plain loop over the 74 segments is a chain of L2 latencies)
+    const float* ml = p.part_ml + slot0 * 2 * TQ + r;
+    const float* po = p.part + (slot0 * 2 * TQ + r) * DH + c;
     float M = -INFINITY;
-#pragma unroll 8
-    for (int s = 0; s < p.segs; ++s) M = fmaxf(M, __ldg(p.part_ml + ((slot0 + s) * 2 + 0) * TQ + r));
+    for (int s0 = 0; s0 < p.segs; s0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) t[a] = (s0 + a < p.segs) ? __ldg(ml + (size_t)(s0 + a) * 2 * TQ) : -INFINITY;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) M = fmaxf(M, t[a]);
+    }
     float L = 0.0f, o = 0.0f;
-#pragma unroll 8      // independent loads in flight: the loop is a chain of L2 latencies otherwise (27 us for 74 segments)
-    for (int s = 0; s < p.segs; ++s) {
-        const float w = ex2(__ldg(p.part_ml + ((slot0 + s) * 2 + 0) * TQ + r) - M);
-        L += w * __ldg(p.part_ml + ((slot0 + s) * 2 + 1) * TQ + r);
-        o += w * __ldg(p.part + ((slot0 + s) * 2 * TQ + r) * DH + c);
+    for (int s0 = 0; s0 < p.segs; s0 += 8) {
+        float tm[8], tl[8], to[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const bool in = s0 + a < p.segs;
+            tm[a] = in ? __ldg(ml + (size_t)(s0 + a) * 2 * TQ) : -INFINITY;
+            tl[a] = in ? __ldg(ml + (size_t)(s0 + a) * 2 * TQ + TQ) : 0.0f;
+            to[a] = in ? __ldg(po + (size_t)(s0 + a) * 2 * TQ * DH) : 0.0f;
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const float w = ex2(tm[a] - M);      // 0 for the padding of the last batch
+            L += w * tl[a];
+            o += w * to[a];
+        }
     }
     if (q < p.S) p.ctx_out[(size_t)q * p.D + h * DH + c] = o / L;
     if (c == 0) p.lse2[(size_t)h * p.S_pad + q] = (q < p.S) ? M + log2f(L) : INFINITY;
@@ -992,8 +1010,14 @@ __global__ void __launch_bounds__(DH) attn_combine_sum_kernel(const AttnParams p
     if (q >= p.S) return;
     const size_t slot0 = (size_t)blockIdx.x * p.segs;
     float o = 0.0f;
-#pragma unroll 8
-    for (int s = 0; s < p.segs; ++s) o += __ldg(p.part + (((slot0 + s) * 2 + arr) * TQ + r) * DH + c);
+    const float* po = p.part + ((slot0 * 2 + arr) * TQ + r) * DH + c;
+    for (int s0 = 0; s0 < p.segs; s0 += 8) {      // 8 loads in flight
+        float t[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) t[a] = (s0 + a < p.segs) ? __ldg(po + (size_t)(s0 + a) * 2 * TQ * DH) : 0.0f;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) o += t[a];
+    }
     p.dqkv[(size_t)q * (3 * p.D) + col0 + h * DH + c] = o * mul;
 }
 

@@ -347,21 +347,31 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
     const Job& jb = p.jobs[blockIdx.z];
     const int m0 = (int)blockIdx.x * 32, n0 = (int)blockIdx.y * 32;
     if (m0 >= jb.M || n0 >= jb.N) return;
-    __shared__ float t[32][33];
+    __shared__ float t_s[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // 16 independent loads in flight per thread (4 columns x 4 k-ranges): as a plain accumulation loop the kernel was a chain
+    // of L2 latencies (48 us for 19 MB of partial sums)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* base = jb.part + (size_t)(n0 + ty) * jb.M + m0 + tx;      // column n0 + ty + 8 j < n_pad (a multiple of 64)
+    const size_t ks_stride = (size_t)jb.n_pad * jb.M, j_stride = (size_t)8 * jb.M;
+    for (int ks = 0; ks < jb.ksplit; ks += 4) {
+        float t[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int n = n0 + ty + 8 * j;      // < n_pad: n_pad is a multiple of 64
-        float acc = 0.0f;
-#pragma unroll 4
-        for (int ks = 0; ks < jb.ksplit; ++ks) acc += __ldg(jb.part + ((size_t)ks * jb.n_pad + n) * jb.M + m0 + tx);
-        t[ty + 8 * j][tx] = acc;
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[a][j] = (ks + a < jb.ksplit) ? __ldg(base + (size_t)(ks + a) * ks_stride + j * j_stride) : 0.0f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += t[a][j];
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t_s[ty + 8 * j][tx] = acc[j];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int m = m0 + ty + 8 * j, n = n0 + tx;
-        if (n < jb.N) jb.out[(long long)m * jb.ldc + n] = t[tx][ty + 8 * j];
+        if (n < jb.N) jb.out[(long long)m * jb.ldc + n] = t_s[tx][ty + 8 * j];
     }
 }
 

@@ -867,8 +867,22 @@ def _wants_stash(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+LSTM_HIDDEN_SIZES = (32, 64, 128, 256, 512)      # the sizes the persistent recurrence kernels are instantiated for
+
+
 def lstm_layer(x, w_ih, w_hh):
-    return LstmLayerFn.apply(x, w_ih, w_hh, _wants_stash(x, w_ih, w_hh))
+    """One bias-free LSTM layer (gate order i, f, g, o; zero initial state) -> hs [B, T, H].
+    Hidden sizes between the instantiated ones run in the next larger kernel with zero-padded weights: a padded unit has
+    zero pre-activations, so its cell and output stay exactly 0 and it feeds nothing back -- the function and (through
+    autograd's pad / slice) every gradient are those of the unpadded layer."""
+    H = w_hh.shape[1]
+    if H in LSTM_HIDDEN_SIZES or H > LSTM_HIDDEN_SIZES[-1]:       # larger sizes: the library reports them as unsupported
+        return LstmLayerFn.apply(x, w_ih, w_hh, _wants_stash(x, w_ih, w_hh))
+    Hp = next(h for h in LSTM_HIDDEN_SIZES if h >= H)
+    pad = torch.nn.functional.pad
+    w_ih_p = pad(w_ih.reshape(4, H, -1), (0, 0, 0, Hp - H)).reshape(4 * Hp, -1)
+    w_hh_p = pad(w_hh.reshape(4, H, H), (0, Hp - H, 0, Hp - H)).reshape(4 * Hp, Hp)
+    return LstmLayerFn.apply(x, w_ih_p, w_hh_p, _wants_stash(x, w_ih, w_hh))[..., :H]
 
 
 def who_to_track(boxes, hs1, w_pred):

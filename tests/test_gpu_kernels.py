@@ -221,6 +221,45 @@ def test_lstm_long_sequence_all_flavours(cuda_device, monkeypatch, flavour, H, T
         assert err <= 1e-4 * scale, (name, err, scale)
 
 
+@pytest.mark.parametrize("H,B,T,I", [(48, 5, 17, 6), (100, 3, 40, 90), (200, 9, 25, 6), (384, 4, 30, 12), (20, 2, 8, 75)])
+def test_lstm_layer_any_hidden_size(cuda_device, H, B, T, I):
+    """Hidden sizes the kernels are not instantiated for run zero-padded in the next larger one (ops.lstm_layer): same
+    function and gradients as the unpadded layer (a kernel generic in H)."""
+    x, w_ih, w_hh, dh = _lstm_case(B, T, I, H, seed=900 + H)
+    xr, wir, whr = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh)]
+    ref = oracle.lstm_layer(xr, wir, whr)
+    ref.backward(dh.double())
+    xg, wig, whg = [t.to(cuda_device).requires_grad_(True) for t in (x, w_ih, w_hh)]
+    out = ops.lstm_layer(xg, wig, whg)
+    assert out.shape == (B, T, H)
+    out.backward(dh.to(cuda_device))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max().item() <= 2e-5
+    for name, got, want in (("dx", xg.grad, xr.grad), ("dw_ih", wig.grad, wir.grad), ("dw_hh", whg.grad, whr.grad)):
+        assert got.shape == want.shape
+        err = (got.cpu().double() - want).abs().max().item()
+        assert err <= 5e-5 * max(1.0, want.abs().max().item()), (name, err)
+
+
+def test_baseline_lstm_with_an_unlisted_hidden_size(cuda_device):
+    """ModelsFactory with videos_hidden_dim = 100 (not a kernel size): forward and parameter gradients against the oracle."""
+    cfg = {"videos_hidden_dim": 100}
+    from objectpermanence_b200.models_factory import ModelsFactory
+    from objectpermanence_b200.synthetic import make_batch
+    boxes_np, labels_np, _ = make_batch(3, 20, 5, seed=77)
+    boxes, labels = torch.from_numpy(boxes_np), torch.from_numpy(labels_np)
+    params = oracle.init_params("baseline_lstm", cfg, seed=3)
+    y_ref, _, _, g_ref = oracle.loss_and_grads("baseline_lstm", params, boxes, labels, cfg, dtype=torch.float64)
+    model = ModelsFactory.get_model("baseline_lstm", cfg).to(cuda_device)
+    model.load_state_dict({k: v.float() for k, v in params.items()})
+    y = model(boxes.to(cuda_device))
+    assert (y.detach().cpu().double() - y_ref).abs().max().item() <= 1e-4
+    loss3, dy = ops.loss_and_grad(y, labels.to(cuda_device), None, False)
+    y.backward(dy)
+    for k, want in g_ref.items():
+        got = dict(model.named_parameters())[k].grad
+        assert (got.cpu().double() - want).abs().max().item() <= 2e-4 * max(1e-3, want.abs().max().item()), k
+
+
 # ---- batch-wide tcgen05 recurrence (opn_lstm_tc.cu): groups of 128 videos, weights in shared memory, TMEM accumulators ----
 @pytest.mark.parametrize("H", [256, 512])
 @pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (40, 9), (128, 6), (130, 17), (256, 5)])
