@@ -189,6 +189,7 @@ typedef struct {
     int64_t lda, ldb, ldc;
     int64_t rows, T, M, N;
     int32_t shift;
+    int32_t trans_out; /* != 0: out is written transposed, [N, M] (ldc >= M) */
 } opn_wgrad_job;
 OPN_API int64_t opn_wgrad_workspace_bytes(int32_t n_jobs, const opn_wgrad_job* jobs);
 OPN_API int opn_wgrad(int32_t n_jobs, const opn_wgrad_job* jobs, void* workspace, int64_t workspace_bytes, void* stream);
@@ -241,6 +242,17 @@ OPN_API int opn_add(int64_t n, const float* a, const float* b, float* out, void*
  * term (the *_no_labels models).  loss_out: 3 floats {total, prediction, consistency}. */
 OPN_API int opn_loss_fwd_bwd(int64_t B, int64_t T, const float* y, const float* labels, const uint8_t* mask, int consistency,
                      float* loss_out, float* dy, void* stream);
+
+/* ---- bbox head + training loss, forward and backward, in one pass --------------------
+ * y [B,T,4] = h [B,T,H] w^T (the bias-free prediction layer, baselines/learned_models.py:33,47,117,150,196), the loss of
+ * opn_loss_fwd_bwd on it, and the backward of both: d_h [B,T,H] = dLoss/dy w, d_w [4,H] = dLoss/dy^T h.  h is read once
+ * and d_h written once (the separate head, loss, dy w and column-reduction launches read h twice at a fraction of the HBM
+ * rate).  H a multiple of 128 up to 512 (OPN_ERR_UNSUPPORTED otherwise: use opn_sgemm + opn_loss_fwd_bwd).
+ * workspace: opn_head_loss_workspace_bytes(B,T,H) bytes (reserved; d_w is accumulated with fp32 reductions). */
+OPN_API int64_t opn_head_loss_workspace_bytes(int64_t B, int64_t T, int64_t H);
+OPN_API int opn_head_loss(int64_t B, int64_t T, int64_t H, const float* h, const float* w, const float* labels, const uint8_t* mask,
+                  int consistency, float* y, float* loss_out, float* d_h, float* d_w, void* workspace, int64_t workspace_bytes,
+                  void* stream);
 
 /* ---- optimiser step (baselines/training_main.py:150,217) ---------------------------
  * torch.optim.Adam (amsgrad off) over one flat fp32 buffer of n parameters, in place:

@@ -23,7 +23,7 @@ _P = c_void_p
 class WgradJob(ctypes.Structure):
     """opn_wgrad_job of include/opnet_b200.h."""
     _fields_ = [("a", c_void_p), ("b", c_void_p), ("out", c_void_p), ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64),
-                ("rows", c_int64), ("T", c_int64), ("M", c_int64), ("N", c_int64), ("shift", c_int32)]
+                ("rows", c_int64), ("T", c_int64), ("M", c_int64), ("N", c_int64), ("shift", c_int32), ("trans_out", c_int32)]
 
 
 SIGNATURES = {
@@ -62,6 +62,8 @@ SIGNATURES = {
     "opn_add": (c_int, [c_int64, _P, _P, _P, _P]),
     "opn_dropout": (c_int, [c_int64, _P, _P, c_float, c_uint64, c_uint64, _P]),
     "opn_loss_fwd_bwd": (c_int, [c_int64, c_int64, _P, _P, _P, c_int, _P, _P, _P]),
+    "opn_head_loss_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "opn_head_loss": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "opn_adam_step": (c_int, [c_int64, _P, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_int64, _P]),
     "opn_iou_eval": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "opn_to_pixels": (c_int, [c_int64, _P, _P, _P]),

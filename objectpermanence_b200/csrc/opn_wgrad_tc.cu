@@ -64,6 +64,7 @@ struct Job {
     int shift;             // 1: row r of `a` meets row r - 1 of `b`; rows with r % T == 0 take no part
     int m_tiles, n_chunks, ksplit, cta0;
     int b_vec;             // rows of `b` are 16-byte aligned: float4 loads
+    int trans_out;         // out is [N][M] (ldc): the partial sums already lie that way
 };
 struct WgradParams {
     Job jobs[kMaxJobs];
@@ -365,6 +366,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[j] += t[a][j];
     }
+    if (jb.trans_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + ty + 8 * j;
+            if (n < jb.N) jb.out[(long long)n * jb.ldc + m0 + tx] = acc[j];
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) t_s[ty + 8 * j][tx] = acc[j];
     __syncthreads();
@@ -401,7 +410,7 @@ int make_plan(int n_jobs, const opn_wgrad_job* jobs, Plan& pl, char* ws) {
         const opn_wgrad_job& u = jobs[j];
         OPN_CHECK_ARG(u.a && u.b && u.out && u.rows > 0 && u.T > 0 && u.M > 0 && u.N > 0, "wgrad: job %d: bad argument", j);
         OPN_CHECK_ARG(u.M % WM == 0, "wgrad: job %d: M = %lld is not a multiple of %d", j, (long long)u.M, WM);
-        OPN_CHECK_ARG(u.lda >= u.M && u.ldb >= u.N && u.ldc >= u.N, "wgrad: job %d: row stride shorter than the row", j);
+        OPN_CHECK_ARG(u.lda >= u.M && u.ldb >= u.N && u.ldc >= (u.trans_out ? u.M : u.N), "wgrad: job %d: row stride shorter than the row", j);
         OPN_CHECK_ARG(u.rows < (1LL << 31) && u.M < (1LL << 24) && u.N < (1LL << 24), "wgrad: job %d: size out of range", j);
         Job& jb = tmp[j];
         jb.a = u.a, jb.b = u.b, jb.out = u.out, jb.part = nullptr;
@@ -411,6 +420,7 @@ int make_plan(int n_jobs, const opn_wgrad_job* jobs, Plan& pl, char* ws) {
         jb.rows_pad = (jb.rows + WK - 1) / WK * WK;
         jb.planes = nullptr;
         jb.shift = u.shift ? 1 : 0;
+        jb.trans_out = u.trans_out ? 1 : 0;
         jb.m_tiles = jb.M / WM;
         jb.n_chunks = (jb.n_pad + WN - 1) / WN;
         jb.b_vec = (u.ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(u.b) & 15) == 0) ? 1 : 0;

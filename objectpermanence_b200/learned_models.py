@@ -94,16 +94,21 @@ class OPNet(AbstractCaterModel, _WhoToTrackMixin):
         self.video_LSTM = LstmWeights(self.bb_in_dim, h2)
         self.prediction_layer = LinearWeights(h2, self.bb_out_dim)
 
-    def forward(self, boxes: torch.Tensor):
+    head_name = "prediction_layer"
+
+    def trunk(self, boxes: torch.Tensor):
+        """Everything in front of the bbox head -> (hidden states [B,T,H2], who-to-track logits [B,15,T])."""
         self._check(boxes)
         l1, l2, wp = self.object_to_track_LSTM, self.video_LSTM, self.object_to_track_prediction.weight
         if ops.opnet_fused_available(l1.hidden_size, l2.hidden_size, wp.shape[0], boxes.shape[0]):
             # one persistent kernel for LSTM1 + who-to-track + LSTM2 (shipped config)
-            h2, logits = ops.opnet_trunk(boxes, l1.weight_ih_l0, l1.weight_hh_l0, wp, l2.weight_ih_l0, l2.weight_hh_l0)
-            return self.prediction_layer(h2), logits
+            return ops.opnet_trunk(boxes, l1.weight_ih_l0, l1.weight_hh_l0, wp, l2.weight_ih_l0, l2.weight_hh_l0)
         frames_boxes, logits = self._track(boxes)
-        y_boxes = self.prediction_layer(self.video_LSTM(frames_boxes))
-        return y_boxes, logits
+        return self.video_LSTM(frames_boxes), logits
+
+    def forward(self, boxes: torch.Tensor):
+        h2, logits = self.trunk(boxes)
+        return self.prediction_layer(h2), logits
 
 
 class OPNetLstmMlp(AbstractCaterModel, _WhoToTrackMixin):
@@ -118,11 +123,16 @@ class OPNetLstmMlp(AbstractCaterModel, _WhoToTrackMixin):
         self.hidden_layer = LinearWeights(self.bb_in_dim, h2)
         self.prediction_layer = LinearWeights(h2, self.bb_out_dim)
 
-    def forward(self, boxes: torch.Tensor):
+    head_name = "prediction_layer"
+
+    def trunk(self, boxes: torch.Tensor):
         self._check(boxes)
         frames_boxes, logits = self._track(boxes)
-        y_boxes = self.prediction_layer(self.hidden_layer(frames_boxes, relu=True))
-        return y_boxes, logits
+        return self.hidden_layer(frames_boxes, relu=True), logits
+
+    def forward(self, boxes: torch.Tensor):
+        h, logits = self.trunk(boxes)
+        return self.prediction_layer(h), logits
 
 
 class BaselineLstm(AbstractCaterModel):
@@ -134,10 +144,15 @@ class BaselineLstm(AbstractCaterModel):
         self.video_LSTM = LstmWeights(self.max_objects_in_frame * self.bb_in_dim, h)
         self.predictions_layer = LinearWeights(h, self.bb_out_dim)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    head_name = "predictions_layer"
+
+    def trunk(self, x: torch.Tensor):
         self._check(x)
         B, T = x.shape[:2]
-        return self.predictions_layer(self.video_LSTM(x.reshape(B, T, -1)))
+        return self.video_LSTM(x.reshape(B, T, -1)), None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.predictions_layer(self.trunk(x)[0])
 
 
 class NonLinearLstm(AbstractCaterModel):
@@ -150,11 +165,16 @@ class NonLinearLstm(AbstractCaterModel):
         self.video_LSTM = LstmWeights(self.max_objects_in_frame * d, h, num_layers=2)
         self.predictions_layer = LinearWeights(h, self.bb_out_dim)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    head_name = "predictions_layer"
+
+    def trunk(self, x: torch.Tensor):
         self._check(x)
         B, T = x.shape[:2]
         feats = self.boxes_linear(x, relu=True)
-        return self.predictions_layer(self.video_LSTM(feats.reshape(B, T, -1)))
+        return self.video_LSTM(feats.reshape(B, T, -1)), None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.predictions_layer(self.trunk(x)[0])
 
 
 class _SelfAttnWeights(nn.Module):
@@ -233,9 +253,14 @@ class TransformerLstm(AbstractCaterModel):
         self.video_LSTM = LstmWeights(d, config["lstm_hidden_dim"], num_layers=config["num_lstm_layers"])
         self.predictions_layer = LinearWeights(config["lstm_hidden_dim"], self.bb_out_dim)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    head_name = "predictions_layer"
+
+    def trunk(self, x: torch.Tensor):
         self._check(x)
         B, T = x.shape[:2]
         snitch = ops.slot_linear_relu(x, self.boxes_linear.weight, 0)      # [B,T,D]
         attended = self.attention_encoder(snitch.reshape(B * T, -1))       # [B*T, D]
-        return self.predictions_layer(self.video_LSTM(attended.reshape(B, T, -1)))
+        return self.video_LSTM(attended.reshape(B, T, -1)), None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.predictions_layer(self.trunk(x)[0])

@@ -364,16 +364,20 @@ def _lstm_recurrence_backward(w_hh, gates, cells, dhs):
 
 
 def wgrad_jobs_run(jobs) -> None:
-    """One launch of opn_wgrad over `jobs` = [(a [rows, M], b [rows, N], out [M, N], T, shift), ...]: out = sum_r a[r]^T
-    b[r - shift] (shift 1: rows with r % T == 0 excluded).  The tcgen05 weight-gradient kernel of csrc/opn_wgrad_tc.cu."""
+    """One launch of opn_wgrad over `jobs` = [(a [rows, M], b [rows, N], out [M, N], T, shift[, trans_out]), ...]: out = sum_r
+    a[r]^T b[r - shift] (shift 1: rows with r % T == 0 excluded; trans_out: `out` is [N, M] and receives the transpose).
+    The tcgen05 weight-gradient kernel of csrc/opn_wgrad_tc.cu."""
     lib = _lib.load()
     arr = (_lib.WgradJob * len(jobs))()
-    for j, (a, b, out, T, shift) in enumerate(jobs):
+    for j, job in enumerate(jobs):
+        a, b, out, T, shift = job[:5]
+        trans_out = bool(job[5]) if len(job) > 5 else False      # out given as [N, M]: written transposed
         rows, M = a.shape
         N = b.shape[1]
-        assert b.shape[0] == rows and out.shape == (M, N) and a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
+        assert b.shape[0] == rows and out.shape == ((N, M) if trans_out else (M, N))
+        assert a.stride(1) == 1 and b.stride(1) == 1 and out.stride(1) == 1
         arr[j] = _lib.WgradJob(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.stride(0), b.stride(0), out.stride(0), rows, T, M, N,
-                               int(shift))
+                               int(shift), int(trans_out))
     n = lib.opn_wgrad_workspace_bytes(len(jobs), arr)
     if n <= 0:
         _lib.check(-1, "opn_wgrad_workspace_bytes")
@@ -604,9 +608,9 @@ class OPNetTrunkFn(torch.autograd.Function):
                 # dW_pred in the transposed orientation (H1 = the 128-wide dimension)
                 j2, dw_ih2, dw_hh2 = _lstm_wgrad_jobs(dgates2, fb, hs2, w_ih2, w_hh2, True, True)
                 j1, dw_ih1, dw_hh1 = _lstm_wgrad_jobs(dgates1, x1, hs1, w_ih1, w_hh1, True, True)
-                dw_pred_t = torch.empty(H1, 15, device=dev, dtype=torch.float32)
-                wgrad_jobs_run(j2 + j1 + [(hs1.reshape(B * T, H1), dl.reshape(B * T, 15), dw_pred_t, T, 0)])
-                return None, dw_ih1, dw_hh1, dw_pred_t.t(), dw_ih2, dw_hh2, None
+                dw_pred = _grad_like(w_pred)
+                wgrad_jobs_run(j2 + j1 + [(hs1.reshape(B * T, H1), dl.reshape(B * T, 15), dw_pred, T, 0, True)])
+                return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2, None
             if os.environ.get("OPN_OPNET_WGRAD_OVERLAP", "1") not in ("0", "") and all(need[1:6]):
                 # The five weight-gradient contractions are independent of each other and none fills the GPU (pre-pass,
                 # 16-64 output tiles, split-K): LSTM2's stay on the main stream, LSTM1's and dW_pred run beside them
@@ -835,6 +839,41 @@ def loss_and_grad(y, labels, mask=None, no_labels: bool = False):
                                       out.data_ptr(), dy.data_ptr(), _stream())
     _lib.check(rc, "opn_loss_fwd_bwd")
     return out, dy
+
+
+def head_loss_available(h: torch.Tensor, weight: torch.Tensor, bias) -> bool:
+    """The fused bbox head + loss pass (opn_head_loss) exists for bias-free heads [4, H] with H a multiple of 128 up to 512;
+    OPN_HEAD_LOSS=0 keeps the separate launches."""
+    H = weight.shape[1]
+    return (bias is None and weight.shape[0] == 4 and H % 128 == 0 and 128 <= H <= 512 and h.dim() == 3 and h.shape[2] == H
+            and os.environ.get("OPN_HEAD_LOSS", "1") not in ("0", ""))
+
+
+def head_loss(h, weight, labels, mask=None, no_labels: bool = False):
+    """Bbox head, training loss and the backward of both in one launch, outside autograd:
+    -> (y [B,T,4], 3-vector (total, prediction, consistency), d total / d h [B,T,H], d total / d weight [4,H]).
+    `h.backward(dh)` continues into the model; dW lands in the weight's registered gradient slot if it has one."""
+    _require_cuda(h, weight, labels)
+    h = h.detach().contiguous()
+    w = weight.detach().contiguous()
+    labels = labels.contiguous()
+    B, T, H = h.shape
+    m = None
+    if no_labels:
+        if mask is None:
+            raise RuntimeError("*_no_labels models need the visibility mask")
+        m = mask.to(torch.uint8).contiguous()
+    lib = _lib.load()
+    y = torch.empty(B, T, 4, device=h.device, dtype=torch.float32)
+    out = torch.empty(3, device=h.device, dtype=torch.float32)
+    dh = torch.empty_like(h)
+    dw = _grad_like(weight)
+    n = lib.opn_head_loss_workspace_bytes(B, T, H)
+    ws = torch.empty(n, dtype=torch.uint8, device=h.device)
+    rc = lib.opn_head_loss(B, T, H, h.data_ptr(), w.data_ptr(), labels.data_ptr(), _ptr(m), int(no_labels), y.data_ptr(),
+                           out.data_ptr(), dh.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, _stream())
+    _lib.check(rc, "opn_head_loss")
+    return y, out, dh, dw
 
 
 class TrainingLossFn(torch.autograd.Function):

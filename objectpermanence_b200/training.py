@@ -55,8 +55,23 @@ class TrainingStep:
         3-vector (total, prediction, consistency) as a device tensor out; nothing synchronises."""
         for p in self.model.parameters():
             p.grad = None
-        out = self.model(boxes)
-        y = out[0] if _is_double_output(self.model_name) else out
+        head = getattr(self.model, getattr(self.model, "head_name", ""), None)
+        if head is not None and hasattr(self.model, "trunk"):
+            # bbox head + loss + their backward as one pass over the hidden states (ops.head_loss) when the shape allows
+            h, _ = self.model.trunk(boxes)
+            if ops.head_loss_available(h, head.weight, head.bias) and head.weight.requires_grad and h.requires_grad:
+                _, loss3, dh, dw = ops.head_loss(h, head.weight, labels, mask, _is_no_labels(self.model_name))
+                head.weight.grad = dw
+                h.backward(dh)
+                if self.reducer is not None:
+                    self.reducer.reduce()
+                if self.optimizer is not None:
+                    self.optimizer.step()
+                return loss3
+            y = head(h)
+        else:
+            out = self.model(boxes)
+            y = out[0] if _is_double_output(self.model_name) else out
         # the loss launch also writes d total / dy: seed the backward pass with it directly (loss3[0].backward() would
         # add autograd's own fill / select / multiply kernels in front of it)
         loss3, dy = ops.loss_and_grad(y, labels, mask, _is_no_labels(self.model_name))

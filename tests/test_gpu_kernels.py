@@ -346,9 +346,14 @@ def test_no_grad_skips_the_stash_even_when_the_weights_require_grad(cuda_device,
 
 
 def test_lstm_unsupported_hidden_size(cuda_device):
-    x, w_ih, w_hh, _ = _lstm_case(2, 3, 6, 48, seed=5)
+    """Hidden sizes up to 512 run (zero-padded into the next kernel size: test_lstm_layer_any_hidden_size); larger ones, and
+    sizes the C ABI is called with directly, are refused with a message, never computed on another path."""
+    x, w_ih, w_hh, _ = _lstm_case(2, 3, 6, 640, seed=5)
     with pytest.raises(_lib.OpnError, match="unsupported"):
         ops.lstm_layer(x.to(cuda_device), w_ih.to(cuda_device), w_hh.to(cuda_device))
+    x, w_ih, w_hh, _ = _lstm_case(2, 3, 6, 48, seed=5)
+    with pytest.raises(_lib.OpnError, match="unsupported"):
+        ops.LstmLayerFn.apply(x.to(cuda_device), w_ih.to(cuda_device), w_hh.to(cuda_device), False)
 
 
 # ---- fused OPNet forward ----------------------------------------------------------------------
@@ -566,11 +571,13 @@ def test_wgrad_tc_kernel(cuda_device, B, T, M, N, shift, mode):
     ad, bd, a2d = a.to(cuda_device), b.to(cuda_device), a2.to(cuda_device)
     out = torch.full((M, N), float("nan"), device=cuda_device)
     out2 = torch.full((M, N + 3), float("nan"), device=cuda_device)      # a strided destination
+    out3 = torch.full((N, M), float("nan"), device=cuda_device)          # the transposed form of job 1
     ops.set_precision(mode)
     try:
-        ops.wgrad_jobs_run([(ad, bd, out, T, shift), (a2d, bd, out2[:, :N], T, 0)])
+        ops.wgrad_jobs_run([(ad, bd, out, T, shift), (a2d, bd, out2[:, :N], T, 0), (ad, bd, out3, T, shift, True)])
     finally:
         ops.set_precision("fp32")
+    assert torch.equal(out3.t(), out)
     torch.cuda.synchronize()
     tol = (3e-5 if mode == "fp32" else 1e-2) * max(1.0, want.abs().max().item())
     assert (out.cpu().double() - want).abs().max().item() <= tol

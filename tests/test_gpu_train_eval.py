@@ -300,3 +300,37 @@ def test_training_step_raises_when_the_status_page_reports_a_timeout(cuda_device
     finally:
         page.zero_()
         ops.set_debug_sync(was_debug)
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 1, 128), (3, 7, 128), (5, 20, 256), (2, 301, 384), (32, 300, 512), (70, 33, 512)])
+@pytest.mark.parametrize("no_labels", [False, True])
+def test_head_loss_kernel_matches_fp64(cuda_device, B, T, H, no_labels):
+    """ops.head_loss (bbox head + loss + backward of both in one pass) against fp64 autograd: y, the loss 3-vector, d h and
+    d W; runs of rows that start / end inside a video, T = 1 (no consistency pairs), the masked *_no_labels form."""
+    from objectpermanence_b200 import ops
+    g = torch.Generator().manual_seed(1000 * H + B * T)
+    h = (torch.rand(B, T, H, generator=g) * 2 - 1)
+    w = (torch.rand(4, H, generator=g) * 2 - 1) / math.sqrt(H)
+    labels = torch.rand(B, T, 4, generator=g)
+    mask = (torch.rand(B, T, 4, generator=g) > 0.3)
+    hr, wr = h.double().requires_grad_(True), w.double().requires_grad_(True)
+    y_ref = hr @ wr.t()
+    if no_labels:
+        pred = ((y_ref - labels.double()).abs() * mask.double()).mean()
+        cons = (y_ref[:, 1:] - y_ref[:, :-1]).norm(dim=-1).mean() if T > 1 else torch.zeros((), dtype=torch.float64)
+        total = pred + 0.5 * cons
+    else:
+        pred = (y_ref - labels.double()).abs().mean()
+        cons = (y_ref[:, 1:] - y_ref[:, :-1]).norm(dim=-1).mean() if T > 1 else torch.zeros((), dtype=torch.float64)
+        total = pred
+    total.backward()
+    assert ops.head_loss_available(h.to(cuda_device), w.to(cuda_device), None)
+    y, loss3, dh, dw = ops.head_loss(h.to(cuda_device), w.to(cuda_device), labels.to(cuda_device), mask.to(cuda_device), no_labels)
+    assert (y.cpu().double() - y_ref.detach()).abs().max().item() <= 2e-6
+    want3 = torch.stack([total.detach(), pred.detach(), cons.detach()])
+    assert (loss3.cpu().double() - want3).abs().max().item() <= 2e-6
+    # sign(y - label) flips where the fp32 head lands on the other side of the label: exclude rows within 1e-5 of a label
+    close = ((y_ref.detach() - labels.double()).abs() < 1e-5).any(dim=-1)
+    err = (dh.cpu().double() - hr.grad).abs().amax(dim=-1)
+    assert err[~close].max().item() <= 1e-6 * max(1.0, hr.grad.abs().max().item()) + 1e-9
+    assert (dw.cpu().double() - wr.grad).abs().max().item() <= 2e-5 * max(1e-3, wr.grad.abs().max().item()) + (2.0 / (B * T * 4)) * close.sum().item()

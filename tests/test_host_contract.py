@@ -151,13 +151,13 @@ def test_workspace_planners_are_pure_host_code():
     rows, T = 9600, 300
     fake = 0x7f0000000000      # never dereferenced by the planner
     spec = [(2048, 512, 1), (2048, 6, 0), (1024, 256, 1), (1024, 90, 0), (256, 15, 0)]
-    jobs = (_lib.WgradJob * len(spec))(*[_lib.WgradJob(fake, fake + 256, fake + 512, M, N, N, rows, T, M, N, sh) for M, N, sh in spec])
+    jobs = (_lib.WgradJob * len(spec))(*[_lib.WgradJob(fake, fake + 256, fake + 512, M, N, N, rows, T, M, N, sh, 0) for M, N, sh in spec])
     n = lib.opn_wgrad_workspace_bytes(len(spec), jobs)
     assert n == lib.opn_wgrad_workspace_bytes(len(spec), jobs)
     # at least the split planes of the small operands (2 planes of bf16, padded to 64 columns) and one partial sum per product
     floor = sum(2 * rows * ((N + 63) // 64 * 64) * 2 + M * ((N + 63) // 64 * 64) * 4 for M, N, _ in spec)
     assert floor <= n <= 8 * floor
-    bad = (_lib.WgradJob * 1)(_lib.WgradJob(fake, fake, fake, 100, 64, 64, rows, T, 100, 64, 0))      # M not a multiple of 128
+    bad = (_lib.WgradJob * 1)(_lib.WgradJob(fake, fake, fake, 100, 64, 64, rows, T, 100, 64, 0, 0))      # M not a multiple of 128
     assert lib.opn_wgrad_workspace_bytes(1, bad) == 0
     assert b"multiple of 128" in lib.opn_last_error()
     # attention: planes of Q', K, V, dO (hi / lo bf16), row statistics, split-row partials, dropout keep bits
