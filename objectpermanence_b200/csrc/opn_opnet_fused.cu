@@ -39,6 +39,8 @@ struct FusedFwdParams {
     float *logits, *probs, *fb;     // [B,15,T], [B,T,15], [B,T,6]
     float *hs2, *gates2, *cells2;   // gates2 / cells2 NULL in inference
     uint32_t *ring1, *ring2;        // [groups][2][8*256], [groups][2][8*512] flagged words, fragment order
+    const unsigned int* fbx;        // EXT mode: [groups][T][8][8] frames_boxes left by the LSTM1 / head producer kernel (ready bit in the LSB)
+    const unsigned int* flags;      // unused (reserved)
     unsigned int* status;
     int B, T;
     int group_offset, n_slices;
@@ -57,6 +59,7 @@ constexpr int KS1 = H1 / 16, KS2 = H2 / 16;
 #define OPN_RING_REPLICAS 1
 #endif
 constexpr int kReplicas = OPN_RING_REPLICAS;
+
 
 // shared memory carve-up (bytes)
 constexpr int OFF_BFRAG2 = 0;                                   // uint4 [KS2*32]
@@ -115,6 +118,12 @@ __device__ __forceinline__ float a_frag_max(const float* ra, const float* rb, in
         m = fmaxf(m, fmaxf(fmaxf(fabsf(a1.x), fabsf(a1.y)), fmaxf(fabsf(a3.x), fabsf(a3.y))));
     }
     return m;
+}
+
+__device__ __forceinline__ unsigned int tc_ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 __device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
@@ -199,7 +208,9 @@ __device__ __forceinline__ int tma_gather(SweepState& st, uint64_t* bars, unsign
 }
 
 // SINGLE: the 1e-2 arithmetic mode (opn_set_precision): the hi.hi product alone, a third of the MMAs
-template <bool SINGLE>
+// EXT: LSTM1 and the who-to-track head run in the producer kernel of opn_opnet_l1head.cu on the SMs this launch leaves idle;
+//      this kernel is then the LSTM2 loop alone and takes frames_boxes[t] from the producer (release flag per frame and slice)
+template <bool SINGLE, bool EXT>
 __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint4* bfrag2_s = reinterpret_cast<uint4*>(smem + OFF_BFRAG2);
@@ -268,8 +279,8 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
     }
 
     // ---- LSTM1 weights: 2 m-tiles x 16 k-steps of A fragments in shared memory; 1024 fragments, 4 per thread ---
-    float winv1, winvp;
-    {
+    float winv1 = 0.0f, winvp = 0.0f;
+    if constexpr (!EXT) {
         auto rows_of = [&](int mt, int gg, const float*& ra, const float*& rb) {
             const int la = mt * 16 + gg, lb = la + 8;
             ra = p.w_hh1 + (size_t)((la & 3) * H1 + u0_1 + (la >> 2)) * H1;
@@ -312,6 +323,8 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
             ap_s[(ks * 2 + 0) * 32 + l] = hi;
             ap_s[(ks * 2 + 1) * 32 + l] = lo;
         }
+    }
+    {
         // ---- W_ih2 rows of the CTA's LSTM2 cells, local row order ----------------------------------------------
         for (int e = tid; e < 64 * 8; e += NT) {
             const int lr = e >> 3, f = e & 7;
@@ -346,7 +359,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
 
     float c1 = 0.0f, c2 = 0.0f;
     float xp0 = 0.f, xp1 = 0.f;
-    if (warp < 4 && valid1) {
+    if (!EXT && warp < 4 && valid1) {
         xp0 = __ldg(xp_ptr);
         xp1 = __ldg(xp_ptr + H1);
     }
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
         store_boxes(i);       // frame i (zeros past the end), read by the head in iteration i+1
         load_boxes(i + 1);
         // ================= LSTM1 frame i + head of frame i-1: both need h1[i-1] ===================================
-        if (i >= 1) {
+        if (i >= 1 && !EXT) {
             // the sweep for h1[i-1] was issued behind the LSTM2 MMAs of the previous iteration (or is issued now)
             const int n = tma_gather<KS1 * 32 / NT>(sw1, bars1, land1_s, bfrag1_s,
                                                     ring1 + (size_t)((i - 1) & 1) * (kGroup * H1), crank,
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
             __syncthreads();
         }
         PH(2);  // h1 tile
-        if (i >= 1) {
+        if (i >= 1 && !EXT) {
             // LSTM1: warp = (m-tile warp&1, K quarter warp>>1), 4 k-steps;  head: k-steps 2*warp, 2*warp+1
             if (i < T) {
                 const int mt1 = warp & 1, kq = warp >> 1;
@@ -439,7 +452,27 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
         // more than the wait they save.)
         if (i >= 2) issue_sweep<KS2 * 32 * 16>(sw2, bars2, land2_s, ring2 + (size_t)((i - 2) & 1) * (kGroup * H2), crank);
         PH(3);  // LSTM1 + head MMAs + barrier
-        if (warp < 4) {
+        if (EXT && i >= 1 && tid < 64) {
+            // frames_boxes[i-1] of this group from the producer kernel (it normally runs frames ahead): words with the ready
+            // bit in the mantissa LSB, polled like the exchange tiles; consumed behind the barrier of the h2 gather
+            const int vb = tid >> 3, f = tid & 7;
+            float x = 0.0f;
+            if (f < NFEAT && vb < nvalid) {
+                const unsigned int* src = p.fbx + (((size_t)group * T + (i - 1)) * 8 + vb) * 8 + f;
+                unsigned int w = ld_relaxed(src);
+                if (!(w & 1u)) {
+                    const long long t0 = clock64();
+                    unsigned spins = 0;
+                    while (!((w = ld_relaxed(src)) & 1u)) {
+                        if ((++spins & 63u) == 0 && poll_expired(t0, p.status, i)) break;
+                    }
+                }
+                x = __uint_as_float(w);
+            }
+            fb_s[tid] = x;
+        }
+        if (EXT) {
+        } else if (warp < 4) {
             if (i < T) {
                 // ---- LSTM1 pointwise, frame i ---------------------------------------------------------------------
                 float a0 = xp0, a1 = xp1;
@@ -489,7 +522,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
                     }
                 }
             }
-        } else if (i >= 1) {
+        } else if (i >= 1 && !EXT) {
             // ---- who-to-track head, frame t = i-1: thread = (video hb, object ho), 16 lanes per video ----------------
             const int t = i - 1;
             float logit = 0.0f;
@@ -559,7 +592,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
         }
         __syncthreads();
         // h1[i] was published before the LSTM2 phase: stream it in while the LSTM2 cells are computed
-        if (i < T) issue_sweep<KS1 * 32 * 16>(sw1, bars1, land1_s, ring1 + (size_t)(i & 1) * (kGroup * H1), crank);
+        if (i < T && !EXT) issue_sweep<KS1 * 32 * 16>(sw1, bars1, land1_s, ring1 + (size_t)(i & 1) * (kGroup * H1), crank);
         PH(6);  // LSTM2 MMAs + barrier
         {
             // ---- LSTM2 pointwise, frame t2: K = 6 input projection from frames_boxes in shared memory -----------
@@ -622,28 +655,87 @@ __global__ void __launch_bounds__(NT, 1) opnet_fwd_fused_kernel(const FusedFwdPa
 }
 
 struct FusedLayout {
-    size_t status_off, ring1_off, ring2_off, total;
+    size_t status_off, ring1_off, ring2_off, flags_off, fbx_off, zero_bytes, total;
 };
-FusedLayout fused_layout(int64_t B) {
+FusedLayout fused_layout(int64_t B, int64_t T) {
     const size_t groups = (size_t)((B + kGroup - 1) / kGroup);
     FusedLayout l;
     l.status_off = 0;
     l.ring1_off = 4096;
     l.ring2_off = l.ring1_off + groups * kReplicas * 2 * kGroup * H1 * sizeof(float);
-    l.total = l.ring2_off + groups * kReplicas * 2 * kGroup * H2 * sizeof(float);
+    l.flags_off = l.ring2_off + groups * kReplicas * 2 * kGroup * H2 * sizeof(float);
+    l.fbx_off = (l.flags_off + groups * (size_t)T * 4 * sizeof(unsigned int) + 255) & ~(size_t)255;
+    l.total = l.fbx_off + groups * (size_t)T * 64 * sizeof(float);
+    l.zero_bytes = l.total;        // status, rings and the ready bits of fbx are zeroed per call
     return l;
+}
+
+// The producer / consumer split (LSTM1 + head on the idle SMs, opn_opnet_l1head.cu) needs both launches co-resident:
+// 32 + 4 CTAs per batch group, one per SM.  OPN_OPNET_SPLIT=0 keeps the single fused kernel.
+bool split_wanted(int64_t B) {
+    const char* e = getenv("OPN_OPNET_SPLIT");
+    if (e && e[0] == '0') return false;
+    // the consumer waits for a producer launched behind it: tools that serialise kernels (Nsight Compute replay,
+    // compute-sanitizer, CUDA_LAUNCH_BLOCKING) would run it to its time-out
+    const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+    if ((lb && lb[0] == '1') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return false;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    const int64_t groups = (B + kGroup - 1) / kGroup;
+    return groups * 37 <= sms;      // 32 consumer + 4 unit + 1 head CTA per batch group, one per SM
+}
+
+// side stream + events of the producer launch, one set per device (created on first use; the library owns them)
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+    static std::mutex mu;
+    static std::map<int, SideStream> per_dev;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream& s = per_dev[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            s.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &s;
 }
 
 }  // namespace
 }  // namespace opn
 
-namespace opn { int current_precision(); }
+namespace opn {
+int current_precision();
+struct L1HeadParams {      // opn_opnet_l1head.cu
+    const float* boxes;
+    const float* xproj1;
+    const float* w_hh1;
+    const float* w_pred;
+    float *hs1, *gates1, *cells1;
+    float *logits, *probs, *fb;
+    uint32_t* fbx;
+    unsigned int* flags;
+    uint32_t* ring1;
+    unsigned int* status;
+    int B, T;
+    int group_offset, n_slices;
+};
+int launch_opnet_l1head(const L1HeadParams& p, int64_t B, bool single, cudaStream_t s);
+int preload_opnet_l1head();
+}  // namespace opn
 using namespace opn;
 
 extern "C" int64_t opn_opnet_fwd_workspace_bytes(int64_t B, int64_t T) {
-    (void)T;
-    if (B <= 0) return 0;
-    return (int64_t)fused_layout(B).total;
+    if (B <= 0 || T <= 0) return 0;
+    return (int64_t)fused_layout(B, T).total;
 }
 
 extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* xproj1,
@@ -662,12 +754,12 @@ extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     OPN_CHECK_ARG((gates1 == nullptr) == (cells1 == nullptr) && (gates2 == nullptr) == (cells2 == nullptr) &&
                       (gates1 == nullptr) == (gates2 == nullptr),
                   "opnet_fwd: the stash tensors must all be given or all NULL");
-    const FusedLayout l = fused_layout(B);
+    const FusedLayout l = fused_layout(B, T);
     OPN_CHECK_ARG(workspace_bytes >= (int64_t)l.total, "opnet_fwd: workspace too small (%lld < %lld)",
                   (long long)workspace_bytes, (long long)l.total);
     cudaStream_t s = as_stream(stream);
     char* ws = static_cast<char*>(workspace);
-    OPN_CUDA(cudaMemsetAsync(ws, 0, l.total, s));
+    OPN_CUDA(cudaMemsetAsync(ws, 0, l.zero_bytes, s));
     FusedFwdParams p;
     p.boxes = boxes;
     p.xproj1 = xproj1;
@@ -691,7 +783,37 @@ extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.T = (int)T;
     p.group_offset = 0;
     p.n_slices = 32;
-    if (current_precision() == OPN_PRECISION_16BIT)
-        return launch_ring(opnet_fwd_fused_kernel<true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
-    return launch_ring(opnet_fwd_fused_kernel<false>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
+    p.fbx = reinterpret_cast<const unsigned int*>(ws + l.fbx_off);
+    p.flags = reinterpret_cast<const unsigned int*>(ws + l.flags_off);
+    const bool single = current_precision() == OPN_PRECISION_16BIT;
+    SideStream* side = split_wanted(B) ? side_stream() : nullptr;
+    if (side) {
+        // consumer (this kernel, LSTM2 alone) on the caller's stream, producer (LSTM1 + head) on the library's side stream:
+        // fork behind the memset and whatever produced the inputs, join so that the caller's stream sees hs1 / logits / ...
+        // the producer's module must be resident before the consumer starts: a lazy load behind a running kernel waits for it
+        // (first call: the consumer ran to its time-out)
+        int rc = preload_opnet_l1head();
+        if (rc != OPN_OK) return rc;
+        OPN_CUDA(cudaEventRecord(side->fork, s));
+        const char* dbg = getenv("OPN_OPNET_SPLIT");
+        const bool producer_only = dbg && dbg[0] == '2';      // timing of the producer alone (tools/split_fwd_debug.py)
+        if (!producer_only)
+        rc = single ? launch_ring(opnet_fwd_fused_kernel<true, true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster)
+                        : launch_ring(opnet_fwd_fused_kernel<false, true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
+        if (rc != OPN_OK) return rc;
+        OPN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        L1HeadParams q;
+        q.boxes = boxes, q.xproj1 = xproj1, q.w_hh1 = w_hh1, q.w_pred = w_pred;
+        q.hs1 = hs1, q.gates1 = gates1, q.cells1 = cells1, q.logits = logits_bpt, q.probs = probs, q.fb = frames_boxes;
+        q.fbx = reinterpret_cast<uint32_t*>(ws + l.fbx_off);
+        q.flags = reinterpret_cast<unsigned int*>(ws + l.flags_off);
+        q.ring1 = p.ring1, q.status = p.status, q.B = (int)B, q.T = (int)T, q.group_offset = 0, q.n_slices = 5;
+        rc = launch_opnet_l1head(q, B, single, side->stream);
+        if (rc != OPN_OK) return rc;
+        OPN_CUDA(cudaEventRecord(side->join, side->stream));
+        OPN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+        return OPN_OK;
+    }
+    if (single) return launch_ring(opnet_fwd_fused_kernel<true, false>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
+    return launch_ring(opnet_fwd_fused_kernel<false, false>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
 }

@@ -356,6 +356,36 @@ def test_lstm_unsupported_hidden_size(cuda_device):
         ops.LstmLayerFn.apply(x.to(cuda_device), w_ih.to(cuda_device), w_hh.to(cuda_device), False)
 
 
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (8, 40), (11, 37), (25, 64), (32, 300)])
+def test_opnet_forward_producer_consumer_split_equals_the_single_kernel(cuda_device, monkeypatch, B, T):
+    """The split forward (LSTM2 loop on 128 CTAs + LSTM1 / who-to-track producer on the idle SMs, opn_opnet_l1head.cu) against
+    the single fused kernel (OPN_OPNET_SPLIT=0): every output of opn_opnet_fwd, ragged groups, T = 1 and 2 (ring slots and the
+    producer's back-pressure from its head CTA), and no time-out on the status page."""
+    lib = _lib.load()
+    H1, H2 = 256, 512
+    g = torch.Generator().manual_seed(17 * B + T)
+    r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1).to(cuda_device)
+    boxes = torch.rand(B, T, 15, 6, generator=g).to(cuda_device)
+    xproj1 = r(B, T, 4 * H1) * 0.5
+    w_hh1, w_pred, w_ih2, w_hh2 = r(4 * H1, H1) / H1 ** 0.5, r(15, H1) / H1 ** 0.5, r(4 * H2, 6) / H2 ** 0.5, r(4 * H2, H2) / H2 ** 0.5
+    shapes = [(B, T, H1), (B, T, 4 * H1), (B, T, H1), (B, 15, T), (B, T, 15), (B, T, 6), (B, T, H2), (B, T, 4 * H2), (B, T, H2)]
+    s = torch.cuda.current_stream().cuda_stream
+    results = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("OPN_OPNET_SPLIT", split)
+        outs = [torch.full(sh, float("nan"), device=cuda_device) for sh in shapes]
+        ws = torch.zeros(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, device=cuda_device)
+        for _ in range(2):      # twice: the second call reuses the zeroed-per-call workspace
+            rc = lib.opn_opnet_fwd(B, T, H1, H2, boxes.data_ptr(), xproj1.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
+                                   w_ih2.data_ptr(), w_hh2.data_ptr(), *[o.data_ptr() for o in outs], ws.data_ptr(), ws.numel(), s)
+            _lib.check(rc, "opn_opnet_fwd")
+        ops.check_status(cuda_device, "opn_opnet_fwd")
+        results[split] = outs
+    for name, a, b in zip(["hs1", "gates1", "cells1", "logits", "probs", "fb", "hs2", "gates2", "cells2"], results["1"], results["0"]):
+        assert not torch.isnan(a).any(), name
+        assert (a - b).abs().max().item() <= 2e-6, name
+
+
 # ---- fused OPNet forward ----------------------------------------------------------------------
 # "fused_inline" after "fused" (two-stream weight gradients, the default) is the order in which [11-37] failed once in
 # round 1; root cause and fix: DESIGN.md section 9 (leftover shared memory read by the fused backward's first sweep)
