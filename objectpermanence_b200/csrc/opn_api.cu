@@ -1,6 +1,10 @@
 // Library-level entry points and host-side error plumbing of libopnet_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <map>
+#include <mutex>
 
 #include "opn_common.cuh"
 
@@ -32,6 +36,41 @@ unsigned int* status_page_or(void* workspace_head) {
 // arithmetic mode of the recurrence / contraction kernels (opn_set_precision)
 static thread_local int g_precision = OPN_PRECISION_FP32;
 int current_precision() { return g_precision; }
+
+// The producer / consumer split (LSTM1 + head on the idle SMs, opn_opnet_l1head.cu) needs both launches co-resident:
+// 32 + 4 CTAs per batch group, one per SM.  OPN_OPNET_SPLIT=0 keeps the single fused kernel.
+bool opnet_split_wanted(int64_t B) {
+    const char* e = getenv("OPN_OPNET_SPLIT");
+    if (e && e[0] == '0') return false;
+    // the consumer waits for a producer launched behind it: tools that serialise kernels (Nsight Compute replay,
+    // compute-sanitizer, CUDA_LAUNCH_BLOCKING) would run it to its time-out
+    const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+    if ((lb && lb[0] == '1') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return false;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    const int64_t groups = (B + 8 - 1) / 8;
+    return groups * 37 <= sms;      // 32 consumer + 4 unit + 1 head CTA per batch group, one per SM
+}
+
+SideStream* opnet_side_stream() {
+    static std::mutex mu;
+    static std::map<int, SideStream> per_dev;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStream& s = per_dev[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            s.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &s;
+}
+
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);

@@ -28,6 +28,16 @@ unsigned int* status_page_or(void* workspace_head);
         if (e__ != cudaSuccess) return opn::cuda_fail(e__, #call); \
     } while (0)
 
+// OPNet forward / backward as two concurrent kernels (the recurrence of LSTM2 on 128 CTAs, LSTM1 + who-to-track on the idle
+// SMs: opn_opnet_l1head.cu, opn_opnet_l1bwd.cu): whether this device / environment allows it for a batch, and the library's
+// side stream with its fork / join events (one set per device, created on first use)
+bool opnet_split_wanted(int64_t B);
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* opnet_side_stream();
+
 // counts kernels launched by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }

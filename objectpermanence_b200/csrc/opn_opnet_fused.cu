@@ -120,12 +120,6 @@ __device__ __forceinline__ float a_frag_max(const float* ra, const float* rb, in
     return m;
 }
 
-__device__ __forceinline__ unsigned int tc_ld_acquire(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
                                                    uint16_t cta_mask) {
     asm volatile(
@@ -670,45 +664,6 @@ FusedLayout fused_layout(int64_t B, int64_t T) {
     return l;
 }
 
-// The producer / consumer split (LSTM1 + head on the idle SMs, opn_opnet_l1head.cu) needs both launches co-resident:
-// 32 + 4 CTAs per batch group, one per SM.  OPN_OPNET_SPLIT=0 keeps the single fused kernel.
-bool split_wanted(int64_t B) {
-    const char* e = getenv("OPN_OPNET_SPLIT");
-    if (e && e[0] == '0') return false;
-    // the consumer waits for a producer launched behind it: tools that serialise kernels (Nsight Compute replay,
-    // compute-sanitizer, CUDA_LAUNCH_BLOCKING) would run it to its time-out
-    const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
-    if ((lb && lb[0] == '1') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return false;
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-    const int64_t groups = (B + kGroup - 1) / kGroup;
-    return groups * 37 <= sms;      // 32 consumer + 4 unit + 1 head CTA per batch group, one per SM
-}
-
-// side stream + events of the producer launch, one set per device (created on first use; the library owns them)
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-SideStream* side_stream() {
-    static std::mutex mu;
-    static std::map<int, SideStream> per_dev;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    SideStream& s = per_dev[dev];
-    if (!s.stream) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
-            (void)cudaGetLastError();
-            s.stream = nullptr;
-            return nullptr;
-        }
-    }
-    return &s;
-}
-
 }  // namespace
 }  // namespace opn
 
@@ -786,7 +741,7 @@ extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.fbx = reinterpret_cast<const unsigned int*>(ws + l.fbx_off);
     p.flags = reinterpret_cast<const unsigned int*>(ws + l.flags_off);
     const bool single = current_precision() == OPN_PRECISION_16BIT;
-    SideStream* side = split_wanted(B) ? side_stream() : nullptr;
+    SideStream* side = opnet_split_wanted(B) ? opnet_side_stream() : nullptr;
     if (side) {
         // consumer (this kernel, LSTM2 alone) on the caller's stream, producer (LSTM1 + head) on the library's side stream:
         // fork behind the memset and whatever produced the inputs, join so that the caller's stream sees hs1 / logits / ...

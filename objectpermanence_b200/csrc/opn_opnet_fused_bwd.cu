@@ -30,10 +30,28 @@ struct FusedBwdParams {
     const float* dhs2;                               // [B,T,512] dLoss / d h2
     float *dgates1, *dgates2, *dl;                   // [B,T,1024], [B,T,2048], [B,T,15]
     uint32_t *ring2, *ring1, *ringf;
+    uint32_t* dfbx;                                  // EXT mode: [groups][T][32][64] shares of d frames_boxes per frame (ready bit)
     unsigned int* status;
     int B, T;
     int group_offset, n_slices;
 };
+
+int current_precision();
+struct L1BwdParams {      // opn_opnet_l1bwd.cu
+    const float *boxes, *probs;
+    const float *w_hh1, *w_pred;
+    const float *gates1, *cells1;
+    float *dgates1, *dl;
+    const uint32_t* dfbx;
+    uint32_t* dhx;
+    uint32_t* ring;
+    unsigned int* status;
+    int B, T;
+    int group_offset, n_slices;
+};
+int launch_opnet_l1bwd(const L1BwdParams& p, int64_t B, bool single, cudaStream_t s);
+int preload_opnet_l1bwd();
+size_t opnet_l1bwd_ring_words_per_group();
 
 namespace {
 
@@ -112,7 +130,10 @@ __device__ __forceinline__ bool take_sweep(uint4 (&v)[NV], const uint4* land, Ad
 __device__ __forceinline__ uint32_t step_parity4(int s) { return ((uint32_t)(s >> 2) & 1u) ^ 1u; }
 
 // SINGLE: the 1e-2 arithmetic mode (opn_set_precision): the hi.hi product alone, a third of the MMAs
-template <bool SINGLE>
+// EXT: the head backward and the LSTM1 reverse recurrence run in the kernel of opn_opnet_l1bwd.cu on the SMs this launch
+//      leaves idle; this kernel is then the LSTM2 loop alone (plain polling of its inbox, as lstm_bwd_mma_kernel<512, 2>) and
+//      leaves its share of d frames_boxes[t] per frame in p.dfbx
+template <bool SINGLE, bool EXT>
 __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint4* a1_s = reinterpret_cast<uint4*>(smem + OFF_A1);
@@ -203,13 +224,16 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
         };
         float m = 0.0f;
         uint4 hi, lo;
-        for (int e = tid; e < 16 * KSB1 * 32; e += NT) frag1(e, 1.0f, hi, lo, m);
-        float wscale1;
-        weight_scale<NW>(m, red_s, wscale1, winv1);
-        for (int e = tid; e < 16 * KSB1 * 32; e += NT) {
-            frag1(e, wscale1, hi, lo, m);
-            a1_s[(e >> 5) * 64 + (e & 31)] = hi;
-            a1_s[(e >> 5) * 64 + 32 + (e & 31)] = lo;
+        winv1 = 0.0f;
+        if constexpr (!EXT) {
+            for (int e = tid; e < 16 * KSB1 * 32; e += NT) frag1(e, 1.0f, hi, lo, m);
+            float wscale1;
+            weight_scale<NW>(m, red_s, wscale1, winv1);
+            for (int e = tid; e < 16 * KSB1 * 32; e += NT) {
+                frag1(e, wscale1, hi, lo, m);
+                a1_s[(e >> 5) * 64 + (e & 31)] = hi;
+                a1_s[(e >> 5) * 64 + 32 + (e & 31)] = lo;
+            }
         }
         // ---- W_ih2^T slice: A[m = feature f (6 of 16)][kk = own row lr] -------------------------------------------
         auto fragx = [&](int e, float scale, uint4& h4, uint4& l4, float& mx) {   // e = ks*32 + lane'
@@ -233,7 +257,8 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
             ax_s[(e >> 5) * 64 + (e & 31)] = hi;
             ax_s[(e >> 5) * 64 + 32 + (e & 31)] = lo;
         }
-        for (int e = tid; e < NOBJ * U1; e += NT) wp_s[e] = __ldg(p.w_pred + (size_t)(e / U1) * H1 + u0_1 + e % U1);
+        if constexpr (!EXT)
+            for (int e = tid; e < NOBJ * U1; e += NT) wp_s[e] = __ldg(p.w_pred + (size_t)(e / U1) * H1 + u0_1 + e % U1);
     }
 
     // ---- cell ownership ------------------------------------------------------------------------------------------
@@ -288,8 +313,8 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
         if (lane < NOBJ) cp_async4(prb_s + (t & 1) * (8 * 16) + warp * 16 + lane, p.probs + ((size_t)(b0 + warp) * T + t) * NOBJ + lane);
     };
     if (valid2) load_stash2(T - 1);
-    if (valid1) load_stash1(T - 1);
-    prefetch_head(T - 1);
+    if (!EXT && valid1) load_stash1(T - 1);
+    if (!EXT) prefetch_head(T - 1);
     int my_abort = 0;
     unsigned nfall2 = 0, nfall1 = 0, nfallf = 0;   // statistics (thread 0 of CTA 0 -> status[8..10]): sweeps that came back stale
     __syncthreads();
@@ -297,6 +322,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
     // iteration s: LSTM2 frame t2 = T-1-s (s < T); head backward + LSTM1 frame t1 = T-s (s >= 1)
     PH_DECL
     for (int s = 0; s <= T; ++s) {
+        if (EXT && s == T) break;
         const int t2 = T - 1 - s, t1 = T - s;
         const int buf = s & 1;
         float v0 = 0.0f, v1 = 0.0f;
@@ -310,10 +336,15 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
                 const uint32_t par = step_parity(sp);
                 uint4 v[4];
                 auto vec_valid = [&](int i) { return warp < nvalid; };
-                cp_async_wait<1>();   // the inbox sweep of the previous iteration; its head prefetch (the last group) may still fly
-                if (!take_sweep(v, land2_s, [&](int i) { return src + ((size_t)warp * NS * 4 + i * 32 + lane) * 4; }, vec_valid, par,
-                                p.status, s, nfall2))
-                    my_abort = 1;
+                if constexpr (EXT) {
+                    if (!gather_flagged(v, [&](int i) { return src + ((size_t)warp * NS * 4 + i * 32 + lane) * 4; }, vec_valid, par, p.status, s))
+                        my_abort = 1;
+                } else {
+                    cp_async_wait<1>();   // the inbox sweep of the previous iteration; its head prefetch (the last group) may still fly
+                    if (!take_sweep(v, land2_s, [&](int i) { return src + ((size_t)warp * NS * 4 + i * 32 + lane) * 4; }, vec_valid, par,
+                                    p.status, s, nfall2))
+                        my_abort = 1;
+                }
                 float r4[4];
                 const bool ok = warp < nvalid;
                 r4[0] = ok ? (__uint_as_float(v[0].x) + __uint_as_float(v[1].x)) + (__uint_as_float(v[2].x) + __uint_as_float(v[3].x)) : 0.f;
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
             }
             PH(0);  // gather + reduce of the LSTM2 partial products
         }
-        if (s >= 1) {
+        if (!EXT && s >= 1) {
             // d frames_boxes shares of frame t1 (published an iteration ago): straight into the summation tile
             const uint32_t* srcf = ringf + (size_t)((s - 1) & 3) * kSlotF;
 #pragma unroll
@@ -423,8 +454,12 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
             const int f = tid >> 3, b = tid & 7;
             const float sum = (dfbp_s[(0 * 8 + f) * 8 + b] + dfbp_s[(1 * 8 + f) * 8 + b]) +
                               (dfbp_s[(2 * 8 + f) * 8 + b] + dfbp_s[(3 * 8 + f) * 8 + b]);
-            st_flagged(ringf + (size_t)(s & 3) * kSlotF + slice * 64 + tid, sum * inv2_s[(2 + buf) * 8 + b], step_parity4(s));
+            if constexpr (EXT)
+                st_flagged(p.dfbx + (((size_t)group * T + t2) * NS + slice) * 64 + tid, sum * inv2_s[(2 + buf) * 8 + b], 1u);
+            else
+                st_flagged(ringf + (size_t)(s & 3) * kSlotF + slice * 64 + tid, sum * inv2_s[(2 + buf) * 8 + b], step_parity4(s));
         }
+        if constexpr (EXT) continue;
         if (warp < 4 && s >= 2) {
             // partial products of LSTM1 step s-2 (published at the end of the previous iteration, a whole LSTM2 phase ago)
             const uint32_t* src1 = ring1 + (size_t)((s - 2) & 3) * kSlot1 + (size_t)slice * kGroup * NS * U1;
@@ -613,29 +648,33 @@ __global__ void __launch_bounds__(NT, 1) opnet_bwd_fused_kernel(const FusedBwdPa
 }
 
 struct FusedBwdLayout {
-    size_t status_off, ring2_off, ring1_off, ringf_off, total;
+    size_t status_off, ring2_off, ring1_off, ringf_off, dfbx_off, dhx_off, ringx_off, total;
 };
-FusedBwdLayout fused_bwd_layout(int64_t B) {
+FusedBwdLayout fused_bwd_layout(int64_t B, int64_t T, bool split) {
     const size_t groups = (size_t)((B + kGroup - 1) / kGroup);
     FusedBwdLayout l;
     l.status_off = 0;
     l.ring2_off = 4096;
     l.ring1_off = l.ring2_off + groups * kSlots2 * kSlot2 * sizeof(float);
-    l.ringf_off = l.ring1_off + groups * kSlots1 * kSlot1 * sizeof(float);
-    l.total = l.ringf_off + groups * kSlotsF * kSlotF * sizeof(float);
+    l.ringf_off = l.ring1_off + (split ? 0 : groups * kSlots1 * kSlot1 * sizeof(float));
+    l.dfbx_off = l.ringf_off + (split ? 0 : groups * kSlotsF * kSlotF * sizeof(float));
+    // split form (opn_opnet_l1bwd.cu): per-frame flagged buffers (no slot reuse, hence no back-pressure) and its small ring
+    l.dhx_off = l.dfbx_off + (split ? groups * (size_t)T * NS * 64 * sizeof(float) : 0);
+    l.ringx_off = l.dhx_off + (split ? groups * (size_t)T * kGroup * H1 * sizeof(float) : 0);
+    l.total = l.ringx_off + (split ? groups * opnet_l1bwd_ring_words_per_group() * sizeof(float) : 0);
     return l;
 }
 
 }  // namespace
 }  // namespace opn
 
-namespace opn { int current_precision(); }
 using namespace opn;
 
 extern "C" int64_t opn_opnet_bwd_workspace_bytes(int64_t B, int64_t T) {
-    (void)T;
-    if (B <= 0) return 0;
-    return (int64_t)fused_bwd_layout(B).total;
+    if (B <= 0 || T <= 0) return 0;
+    // the larger of the two forms: which one runs is decided per call (environment, device)
+    const size_t a = fused_bwd_layout(B, T, false).total, b = fused_bwd_layout(B, T, true).total;
+    return (int64_t)(a > b ? a : b);
 }
 
 extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* probs,
@@ -652,7 +691,8 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     OPN_CHECK_ARG(boxes && probs && w_hh1 && w_pred && w_ih2 && w_hh2 && gates1 && cells1 && gates2 && cells2 && dhs2 && dgates1 &&
                       dgates2 && d_logits && workspace,
                   "opnet_bwd: null pointer");
-    const FusedBwdLayout l = fused_bwd_layout(B);
+    SideStream* side = opnet_split_wanted(B) ? opnet_side_stream() : nullptr;
+    const FusedBwdLayout l = fused_bwd_layout(B, T, side != nullptr);
     OPN_CHECK_ARG(workspace_bytes >= (int64_t)l.total, "opnet_bwd: workspace too small (%lld < %lld)",
                   (long long)workspace_bytes, (long long)l.total);
     cudaStream_t s = as_stream(stream);
@@ -667,10 +707,37 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
     p.ring2 = reinterpret_cast<uint32_t*>(ws + l.ring2_off);
     p.ring1 = reinterpret_cast<uint32_t*>(ws + l.ring1_off);
     p.ringf = reinterpret_cast<uint32_t*>(ws + l.ringf_off);
+    p.dfbx = reinterpret_cast<uint32_t*>(ws + l.dfbx_off);
     p.status = status_page_or(ws + l.status_off);
     p.B = (int)B, p.T = (int)T;
     p.group_offset = 0, p.n_slices = NS;
-    if (current_precision() == OPN_PRECISION_16BIT)
-        return launch_ring(opnet_bwd_fused_kernel<true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
-    return launch_ring(opnet_bwd_fused_kernel<false>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+    const bool single = current_precision() == OPN_PRECISION_16BIT;
+    if (side) {
+        // the LSTM2 loop (this kernel) on the caller's stream, head backward + LSTM1 on the library's side stream (see
+        // opn_opnet_fwd): fork behind the memset and whatever produced the inputs, join so that the caller's stream sees
+        // d_gates1 / d_logits
+        int rc = preload_opnet_l1bwd();
+        if (rc != OPN_OK) return rc;
+        OPN_CUDA(cudaEventRecord(side->fork, s));
+        rc = single ? launch_ring(opnet_bwd_fused_kernel<true, true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd")
+                    : launch_ring(opnet_bwd_fused_kernel<false, true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+        if (rc != OPN_OK) return rc;
+        const char* dbg = getenv("OPN_OPNET_SPLIT");
+        if (dbg && dbg[0] == '3') return OPN_OK;      // timing of the LSTM2 loop alone (tools/split_bwd_debug.py); d_gates1 / d_logits unwritten
+        OPN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        L1BwdParams q;
+        q.boxes = boxes, q.probs = probs, q.w_hh1 = w_hh1, q.w_pred = w_pred, q.gates1 = gates1, q.cells1 = cells1;
+        q.dgates1 = dgates1, q.dl = d_logits;
+        q.dfbx = p.dfbx;
+        q.dhx = reinterpret_cast<uint32_t*>(ws + l.dhx_off);
+        q.ring = reinterpret_cast<uint32_t*>(ws + l.ringx_off);
+        q.status = p.status, q.B = (int)B, q.T = (int)T, q.group_offset = 0, q.n_slices = 5;
+        rc = launch_opnet_l1bwd(q, B, single, side->stream);
+        if (rc != OPN_OK) return rc;
+        OPN_CUDA(cudaEventRecord(side->join, side->stream));
+        OPN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+        return OPN_OK;
+    }
+    if (single) return launch_ring(opnet_bwd_fused_kernel<true, false>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+    return launch_ring(opnet_bwd_fused_kernel<false, false>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
 }
