@@ -386,6 +386,42 @@ def test_opnet_forward_producer_consumer_split_equals_the_single_kernel(cuda_dev
         assert (a - b).abs().max().item() <= 2e-6, name
 
 
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 2), (8, 40), (11, 37), (25, 64), (32, 300)])
+def test_opnet_backward_two_kernel_split_equals_the_single_kernel(cuda_device, monkeypatch, B, T):
+    """The split backward (LSTM2 loop on 128 CTAs + head backward / LSTM1 reverse recurrence on the idle SMs,
+    opn_opnet_l1bwd.cu) against the single fused kernel (OPN_OPNET_SPLIT=0): d_gates1, d_gates2, d_logits; ragged groups, T = 1
+    and 2, twice per workspace, no time-out on the status page."""
+    lib = _lib.load()
+    H1, H2 = 256, 512
+    g = torch.Generator().manual_seed(29 * B + T)
+    R = lambda *s: torch.rand(*s, generator=g).to(cuda_device)
+    boxes = R(B, T, 15, 6)
+    probs = torch.softmax(torch.randn(B, T, 15, generator=g), -1).to(cuda_device)
+    w_hh1, w_pred = (R(4 * H1, H1) * 2 - 1) / H1 ** 0.5, (R(15, H1) * 2 - 1) / H1 ** 0.5
+    w_ih2, w_hh2 = (R(4 * H2, 6) * 2 - 1) / H2 ** 0.5, (R(4 * H2, H2) * 2 - 1) / H2 ** 0.5
+    g1, g2 = R(B, T, 4 * H1), R(B, T, 4 * H2)
+    g1[..., 2 * H1:3 * H1] = g1[..., 2 * H1:3 * H1] * 2 - 1      # the g gate is a tanh
+    g2[..., 2 * H2:3 * H2] = g2[..., 2 * H2:3 * H2] * 2 - 1
+    c1, c2 = torch.randn(B, T, H1, generator=g).to(cuda_device) * 0.5, torch.randn(B, T, H2, generator=g).to(cuda_device) * 0.5
+    dh2 = torch.randn(B, T, H2, generator=g).to(cuda_device) * 0.01
+    s = torch.cuda.current_stream().cuda_stream
+    results = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("OPN_OPNET_SPLIT", split)
+        outs = [torch.full(sh, float("nan"), device=cuda_device) for sh in ((B, T, 4 * H1), (B, T, 4 * H2), (B, T, 15))]
+        ws = torch.zeros(lib.opn_opnet_bwd_workspace_bytes(B, T), dtype=torch.uint8, device=cuda_device)
+        for _ in range(2):
+            rc = lib.opn_opnet_bwd(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(), w_ih2.data_ptr(),
+                                   w_hh2.data_ptr(), g1.data_ptr(), c1.data_ptr(), g2.data_ptr(), c2.data_ptr(), dh2.data_ptr(),
+                                   *[o.data_ptr() for o in outs], ws.data_ptr(), ws.numel(), s)
+            _lib.check(rc, "opn_opnet_bwd")
+        ops.check_status(cuda_device, "opn_opnet_bwd")
+        results[split] = outs
+    for name, a, b in zip(["d_gates1", "d_gates2", "d_logits"], results["1"], results["0"]):
+        assert not torch.isnan(a).any(), name
+        assert (a - b).abs().max().item() <= 2e-6 * max(1e-6, b.abs().max().item()) + 1e-12, name
+
+
 # ---- fused OPNet forward ----------------------------------------------------------------------
 # "fused_inline" after "fused" (two-stream weight gradients, the default) is the order in which [11-37] failed once in
 # round 1; root cause and fix: DESIGN.md section 9 (leftover shared memory read by the fused backward's first sweep)
