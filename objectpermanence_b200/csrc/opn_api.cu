@@ -48,8 +48,15 @@ bool opnet_split_wanted(int64_t B) {
     if ((lb && lb[0] == '1') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return false;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-    const int64_t groups = (B + 8 - 1) / 8;
-    return groups * 37 <= sms;      // 32 consumer + 4 unit + 1 head CTA per batch group, one per SM
+    (void)B;
+    return sms >= 37;      // 32 consumer + 4 unit + 1 head CTA per batch group, one per SM: at least one group per wave
+}
+
+// batch groups per wave of the split form: consumer and producer launches of a wave are co-resident
+int opnet_split_groups_per_wave() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+    return sms / 37 > 0 ? sms / 37 : 1;
 }
 
 SideStream* opnet_side_stream() {

@@ -32,6 +32,7 @@ unsigned int* status_page_or(void* workspace_head);
 // SMs: opn_opnet_l1head.cu, opn_opnet_l1bwd.cu): whether this device / environment allows it for a batch, and the library's
 // side stream with its fork / join events (one set per device, created on first use)
 bool opnet_split_wanted(int64_t B);
+int opnet_split_groups_per_wave();
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;

@@ -179,9 +179,10 @@ int max_coresident(Kernel kernel, int threads, size_t smem, int* out) {
 // cooperative launches of as many whole batch groups as fit on the device.
 // cluster_size > 1: the CTAs are additionally grouped into thread-block clusters of that many consecutive slices
 // (n_slices must be a multiple of it): cooperative launch + cluster dimension.
+// group_begin / group_end: only the batch groups [group_begin, group_end) (default: all of them)
 template <typename Kernel, typename Params>
 int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem, int64_t B, cudaStream_t stream,
-                const char* what, int cluster_size = 1) {
+                const char* what, int cluster_size = 1, int group_begin = 0, int group_end = -1) {
     // the capacity of the device for this kernel is queried once (the occupancy calls cost 0.1-1 ms of host time each)
     static std::mutex cache_mutex;
     static std::map<std::pair<const void*, int>, int> cap_cache;   // (kernel, device) -> co-resident CTAs
@@ -217,14 +218,15 @@ int launch_ring(Kernel kernel, Params p, int threads, int n_slices, size_t smem,
         std::lock_guard<std::mutex> lock(cache_mutex);
         cap_cache[key] = cap;
     }
-    const int groups = (int)((B + kGroup - 1) / kGroup);
+    int groups = (int)((B + kGroup - 1) / kGroup);
+    if (group_end >= 0 && group_end < groups) groups = group_end;
     const int per_launch = cap / n_slices;
     if (per_launch < 1) {
         set_error("%s: device cannot co-schedule %d CTAs (capacity %d)", what, n_slices, cap);
         return OPN_ERR_UNSUPPORTED;
     }
     p.n_slices = n_slices;
-    for (int g0 = 0; g0 < groups; g0 += per_launch) {
+    for (int g0 = group_begin; g0 < groups; g0 += per_launch) {
         const int ng = groups - g0 < per_launch ? groups - g0 : per_launch;
         p.group_offset = g0;
         if (cluster_size > 1) {

@@ -683,7 +683,7 @@ struct L1HeadParams {      // opn_opnet_l1head.cu
     int B, T;
     int group_offset, n_slices;
 };
-int launch_opnet_l1head(const L1HeadParams& p, int64_t B, bool single, cudaStream_t s);
+int launch_opnet_l1head(const L1HeadParams& p, int64_t B, bool single, cudaStream_t s, int group_begin, int group_end);
 int preload_opnet_l1head();
 }  // namespace opn
 using namespace opn;
@@ -750,21 +750,28 @@ extern "C" int opn_opnet_fwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
         int rc = preload_opnet_l1head();
         if (rc != OPN_OK) return rc;
         OPN_CUDA(cudaEventRecord(side->fork, s));
+        OPN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         const char* dbg = getenv("OPN_OPNET_SPLIT");
         const bool producer_only = dbg && dbg[0] == '2';      // timing of the producer alone (tools/split_fwd_debug.py)
-        if (!producer_only)
-        rc = single ? launch_ring(opnet_fwd_fused_kernel<true, true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster)
-                        : launch_ring(opnet_fwd_fused_kernel<false, true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster);
-        if (rc != OPN_OK) return rc;
-        OPN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         L1HeadParams q;
         q.boxes = boxes, q.xproj1 = xproj1, q.w_hh1 = w_hh1, q.w_pred = w_pred;
         q.hs1 = hs1, q.gates1 = gates1, q.cells1 = cells1, q.logits = logits_bpt, q.probs = probs, q.fb = frames_boxes;
         q.fbx = reinterpret_cast<uint32_t*>(ws + l.fbx_off);
         q.flags = reinterpret_cast<unsigned int*>(ws + l.flags_off);
         q.ring1 = p.ring1, q.status = p.status, q.B = (int)B, q.T = (int)T, q.group_offset = 0, q.n_slices = 5;
-        rc = launch_opnet_l1head(q, B, single, side->stream);
-        if (rc != OPN_OK) return rc;
+        // waves of as many batch groups as fit with both kernels co-resident (4 on 148 SMs); the consumer launches queue on the
+        // caller's stream, the producer launches on the side stream: wave k+1 of either starts when its wave k ends
+        const int groups = (int)((B + kGroup - 1) / kGroup), per_wave = opnet_split_groups_per_wave();
+        for (int g0 = 0; g0 < groups; g0 += per_wave) {
+            const int g1 = g0 + per_wave < groups ? g0 + per_wave : groups;
+            if (!producer_only) {
+                rc = single ? launch_ring(opnet_fwd_fused_kernel<true, true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster, g0, g1)
+                            : launch_ring(opnet_fwd_fused_kernel<false, true>, p, NT, 32, (size_t)SMEM_BYTES, B, s, "opnet_fwd", kCluster, g0, g1);
+                if (rc != OPN_OK) return rc;
+            }
+            rc = launch_opnet_l1head(q, B, single, side->stream, g0, g1);
+            if (rc != OPN_OK) return rc;
+        }
         OPN_CUDA(cudaEventRecord(side->join, side->stream));
         OPN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
         return OPN_OK;

@@ -49,7 +49,8 @@ struct L1BwdParams {      // opn_opnet_l1bwd.cu
     int B, T;
     int group_offset, n_slices;
 };
-int launch_opnet_l1bwd(const L1BwdParams& p, int64_t B, bool single, cudaStream_t s);
+int launch_opnet_l1bwd(const L1BwdParams& p, int64_t B, bool single, cudaStream_t s, int group_begin, int group_end);
+int opnet_split_groups_per_wave();
 int preload_opnet_l1bwd();
 size_t opnet_l1bwd_ring_words_per_group();
 
@@ -719,12 +720,9 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
         int rc = preload_opnet_l1bwd();
         if (rc != OPN_OK) return rc;
         OPN_CUDA(cudaEventRecord(side->fork, s));
-        rc = single ? launch_ring(opnet_bwd_fused_kernel<true, true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd")
-                    : launch_ring(opnet_bwd_fused_kernel<false, true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
-        if (rc != OPN_OK) return rc;
-        const char* dbg = getenv("OPN_OPNET_SPLIT");
-        if (dbg && dbg[0] == '3') return OPN_OK;      // timing of the LSTM2 loop alone (tools/split_bwd_debug.py); d_gates1 / d_logits unwritten
         OPN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        const char* dbg = getenv("OPN_OPNET_SPLIT");
+        const bool lstm2_only = dbg && dbg[0] == '3';      // timing of the LSTM2 loop alone (tools/split_bwd_debug.py); d_gates1 / d_logits unwritten
         L1BwdParams q;
         q.boxes = boxes, q.probs = probs, q.w_hh1 = w_hh1, q.w_pred = w_pred, q.gates1 = gates1, q.cells1 = cells1;
         q.dgates1 = dgates1, q.dl = d_logits;
@@ -732,8 +730,18 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
         q.dhx = reinterpret_cast<uint32_t*>(ws + l.dhx_off);
         q.ring = reinterpret_cast<uint32_t*>(ws + l.ringx_off);
         q.status = p.status, q.B = (int)B, q.T = (int)T, q.group_offset = 0, q.n_slices = 5;
-        rc = launch_opnet_l1bwd(q, B, single, side->stream);
-        if (rc != OPN_OK) return rc;
+        // waves of co-resident launches, as in opn_opnet_fwd
+        const int groups = (int)((B + kGroup - 1) / kGroup), per_wave = opnet_split_groups_per_wave();
+        for (int g0 = 0; g0 < groups; g0 += per_wave) {
+            const int g1 = g0 + per_wave < groups ? g0 + per_wave : groups;
+            rc = single ? launch_ring(opnet_bwd_fused_kernel<true, true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd", 1, g0, g1)
+                        : launch_ring(opnet_bwd_fused_kernel<false, true>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd", 1, g0, g1);
+            if (rc != OPN_OK) return rc;
+            if (!lstm2_only) {
+                rc = launch_opnet_l1bwd(q, B, single, side->stream, g0, g1);
+                if (rc != OPN_OK) return rc;
+            }
+        }
         OPN_CUDA(cudaEventRecord(side->join, side->stream));
         OPN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
         return OPN_OK;

@@ -371,9 +371,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1bwd_kernel(const L1BwdParams p)
 }  // namespace l1b
 }  // namespace
 
-int launch_opnet_l1bwd(const L1BwdParams& p, int64_t B, bool single, cudaStream_t s) {
-    if (single) return launch_ring(l1b::opnet_l1bwd_kernel<true>, p, l1b::NT, l1b::NSL + 1, (size_t)l1b::SMEM_BYTES, B, s, "opnet_l1bwd");
-    return launch_ring(l1b::opnet_l1bwd_kernel<false>, p, l1b::NT, l1b::NSL + 1, (size_t)l1b::SMEM_BYTES, B, s, "opnet_l1bwd");
+int launch_opnet_l1bwd(const L1BwdParams& p, int64_t B, bool single, cudaStream_t s, int group_begin, int group_end) {
+    if (single)
+        return launch_ring(l1b::opnet_l1bwd_kernel<true>, p, l1b::NT, l1b::NSL + 1, (size_t)l1b::SMEM_BYTES, B, s, "opnet_l1bwd", 1, group_begin, group_end);
+    return launch_ring(l1b::opnet_l1bwd_kernel<false>, p, l1b::NT, l1b::NSL + 1, (size_t)l1b::SMEM_BYTES, B, s, "opnet_l1bwd", 1, group_begin, group_end);
 }
 
 // loads both variants of the kernel before the LSTM2 kernel starts (a lazy module load behind a running kernel waits for it)

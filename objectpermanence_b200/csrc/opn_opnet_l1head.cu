@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1head_kernel(const L1HeadParams 
 }  // namespace
 
 // host side: called by opn_opnet_fwd (opn_opnet_fused.cu)
-int launch_opnet_l1head(const L1HeadParams& p, int64_t B, bool single, cudaStream_t s) {
-    if (single) return launch_ring(l1::opnet_l1head_kernel<true>, p, l1::NT, l1::NSL + 1, (size_t)l1::SMEM_BYTES, B, s, "opnet_l1head");
-    return launch_ring(l1::opnet_l1head_kernel<false>, p, l1::NT, l1::NSL + 1, (size_t)l1::SMEM_BYTES, B, s, "opnet_l1head");
+int launch_opnet_l1head(const L1HeadParams& p, int64_t B, bool single, cudaStream_t s, int group_begin, int group_end) {
+    if (single)
+        return launch_ring(l1::opnet_l1head_kernel<true>, p, l1::NT, l1::NSL + 1, (size_t)l1::SMEM_BYTES, B, s, "opnet_l1head", 1, group_begin, group_end);
+    return launch_ring(l1::opnet_l1head_kernel<false>, p, l1::NT, l1::NSL + 1, (size_t)l1::SMEM_BYTES, B, s, "opnet_l1head", 1, group_begin, group_end);
 }
 
 
