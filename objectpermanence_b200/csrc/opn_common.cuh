@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/opnet_b200.h"
 
 namespace opn {
@@ -36,6 +38,7 @@ int opnet_split_groups_per_wave();
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    std::mutex enqueue;      // held from the fork record to the join wait: host threads sharing a device take turns
 };
 SideStream* opnet_side_stream();
 

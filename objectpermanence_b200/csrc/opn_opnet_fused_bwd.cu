@@ -719,6 +719,7 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
         // d_gates1 / d_logits
         int rc = preload_opnet_l1bwd();
         if (rc != OPN_OK) return rc;
+        std::lock_guard<std::mutex> turn(side->enqueue);
         OPN_CUDA(cudaEventRecord(side->fork, s));
         OPN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
         const char* dbg = getenv("OPN_OPNET_SPLIT");
