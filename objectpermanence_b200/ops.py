@@ -112,7 +112,14 @@ def _grad_like(weight: torch.Tensor) -> torch.Tensor:
     return torch.empty_like(weight)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw getter: 0.3 us instead of 20 us through
+    torch.cuda.current_stream(), five times per step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
