@@ -42,9 +42,9 @@ constexpr size_t kSlot = (size_t)NSL * NSL * kGroup * U;      // words per ring 
 
 // shared memory carve-up (bytes); the head CTA reuses the first region for its own tiles
 constexpr int OFF_ALO = 0;                                  // uint4 [MT][KS][32]   lo plane of the W_hh1^T fragments, 128 KB
-constexpr int OFF_DA = OFF_ALO + MT * KS * 32 * 16;         // uint4 [KS*32]        scaled d gates1 fragments
-constexpr int OFF_INV = OFF_DA + KS * 32 * 16;              // float [8]
-constexpr int OFF_RED = OFF_INV + 32;                       // float [8]
+constexpr int OFF_DA = OFF_ALO + MT * KS * 32 * 16;         // uint4 [2][KS*32]     scaled d gates1 fragments, double buffered by step
+constexpr int OFF_INV = OFF_DA + 2 * KS * 32 * 16;          // float [2][8]
+constexpr int OFF_RED = OFF_INV + 64;                       // float [8]
 constexpr int SMEM_BYTES = OFF_RED + 64;
 // head CTA
 constexpr int HOFF_WP = 0;                                  // float [15][256]
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1bwd_kernel(const L1BwdParams p)
     const int u0 = slice * U;
     uint32_t* ring = p.ring + (size_t)group * (2 * kSlot);
 
-    for (int i = tid; i < KS * 32; i += NT) da_s[i] = make_uint4(0u, 0u, 0u, 0u);      // absent videos stay zero
+    for (int i = tid; i < 2 * KS * 32; i += NT) da_s[i] = make_uint4(0u, 0u, 0u, 0u);      // absent videos stay zero
     // ---- W_hh1^T slice: A[m = column k][kk = own local row lr = unit*4 + gate]; warp w owns columns 32w .. 32w+31 ------------
     auto wrow = [&](int lr) { return p.w_hh1 + (size_t)((lr & 3) * H1 + u0 + (lr >> 2)) * H1; };
     auto frag = [&](int mt, int ks, int l, float scale, uint4& hi, uint4& lo, float& m) {
@@ -312,28 +312,22 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1bwd_kernel(const L1BwdParams p)
                         const int lr = (ul + j) * 4 + 2 * h2;
                         uint32_t hi, lo;
                         split2(dgv[j][2 * h2] * sc, dgv[j][2 * h2 + 1] * sc, hi, lo);
-                        uint32_t* w = reinterpret_cast<uint32_t*>(da_s) + 4 * ((lr >> 4) * 32 + bl * 4 + (((lr & 15) & 7) >> 1)) + ((lr & 15) >> 3);
+                        uint32_t* w = reinterpret_cast<uint32_t*>(da_s + (s & 1) * (KS * 32)) + 4 * ((lr >> 4) * 32 + bl * 4 + (((lr & 15) & 7) >> 1)) + ((lr & 15) >> 3);
                         w[0] = hi;
                         w[2] = lo;
                     }
-                if (lane == 0) inv_s[bl] = inv * winv;
+                if (lane == 0) inv_s[(s & 1) * 8 + bl] = inv * winv;
             }
         }
         PH(2);  // cells + fragments
         if (__syncthreads_or(my_abort)) break;      // B fragments of all videos complete
         PH(3);  // barrier
-        // d gates1 of frame t (exact), off the critical path of the others
-        if (valid) {
-            float* dg = p.dgates1 + (row0 + t) * (size_t)(4 * H1) + uu;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(dg + q * H1) = make_float2(dgv[0][q], dgv[1][q]);
-        }
         if (t > 0) {
             // partial[k][b] = sum over own rows of W_hh1[row][k] * d gates1[b][row]: 2 m-tiles of 16 columns per warp
             float dm[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, ds[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const uint4 b = da_s[ks * 32 + lane];
+                const uint4 b = da_s[(s & 1) * (KS * 32) + ks * 32 + lane];
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
                     mma4(dm[m], ahi[m][ks], b.x, b.y);
@@ -347,7 +341,7 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1bwd_kernel(const L1BwdParams p)
             // ring word [consumer][producer = slice][video][unit]
             const uint32_t par = step_parity(s);
             uint32_t* pub = ring + (size_t)(s & 1) * kSlot;
-            const float inv0 = inv_s[2 * tq], inv1 = inv_s[2 * tq + 1];
+            const float inv0 = inv_s[(s & 1) * 8 + 2 * tq], inv1 = inv_s[(s & 1) * 8 + 2 * tq + 1];
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -355,10 +349,16 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1bwd_kernel(const L1BwdParams p)
                     const int k = (2 * warp + m) * 16 + g + 8 * (q >> 1), b = 2 * tq + (q & 1);
                     st_flagged(pub + ((size_t)((k >> 6) * NSL + slice) * kGroup + b) * U + (k & 63), (dm[m][q] + ds[m][q]) * ((q & 1) ? inv1 : inv0), par);
                 }
-            // the fragments and scales are rewritten by the next step's cells: every warp must be done reading them
-            __syncthreads();
+            // the fragments and scales of the NEXT step go to the other buffer; the one read here is rewritten two steps on,
+            // behind the next step's barrier: no second barrier per step
         }
-        PH(4);  // MMAs + publish (+ barrier)
+        // d gates1 of frame t (exact), behind the publish: off the critical path of the other CTAs
+        if (valid) {
+            float* dg = p.dgates1 + (row0 + t) * (size_t)(4 * H1) + uu;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(dg + q * H1) = make_float2(dgv[0][q], dgv[1][q]);
+        }
+        PH(4);  // MMAs + publish + d gates stores
     }
 #ifdef OPN_LSTM_PHASES
     if (threadIdx.x == 0 && blockIdx.x == 0) {      // behind the fused kernel's own counters (words 32.., 64..)
