@@ -4,7 +4,7 @@
 // Why: opn_opnet_fused.cu runs LSTM1, the head and LSTM2 on the same 128 CTAs so that each layer's exchange wait hides the
 // other's work -- but the LSTM1 / head work of a frame (2,690 clocks: gather-split, 144 MMAs, cells, softmax) is longer
 // than the h2 exchange it hides, so a frame costs the SUM of both layers' busy phases (6,020 clocks).  Without that work
-// on its SMs the same loop runs at 2.41 us per frame instead of 3.30 (tools/fused_l2only_probe.py).  The 128-CTA launch
+// on its SMs the same loop runs at 2.41 us per frame instead of 3.30 (profiles/r02_fused_l2only_probe.log).  The 128-CTA launch
 // leaves 20 of the 148 SMs idle; this kernel puts LSTM1 + head there: 5 CTAs per batch group of 8 videos -- four with 64
 // hidden units each and one for the who-to-track head -- and the fused kernel (EXT mode) only consumes frames_boxes[t]
 // as it becomes available.
