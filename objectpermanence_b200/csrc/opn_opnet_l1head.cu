@@ -264,21 +264,17 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1head_kernel(const L1HeadParams 
             alo_s[((2 * warp + m) * KS + ks) * 32 + lane] = lo;
         }
     }
-    // ---- cells: two per thread, cell c = tid + 256 j: unit c & 63 (consecutive lanes = consecutive units), video c >> 6 --------
-    int ul[2], bl[2];
-    bool valid[2];
-    size_t row[2];
+    // ---- cells: warp = video, lane = units 2*lane, 2*lane + 1: every load / store of the two cells is one 8-byte access
+    // (x-projection, stash, the published pair of ring words), half the memory instructions of two unrelated cells
+    const int bl = warp, ul = 2 * lane;
+    const bool valid = b0 + bl < p.B;
+    const size_t row0 = (size_t)(valid ? b0 + bl : 0) * T;
+    const int uu = u0 + ul;
     float cst[2] = {0.0f, 0.0f};
-    float xp[2][4];
+    float2 xp[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int c = tid + NT * j;
-        ul[j] = c & 63, bl[j] = c >> 6;
-        valid[j] = b0 + bl[j] < p.B;
-        row[j] = (size_t)(valid[j] ? b0 + bl[j] : 0) * T;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) xp[j][q] = valid[j] ? __ldg(p.xproj1 + row[j] * (4 * H1) + q * H1 + u0 + ul[j]) : 0.0f;
-    }
+    for (int q = 0; q < 4; ++q) xp[q] = valid ? __ldg(reinterpret_cast<const float2*>(p.xproj1 + row0 * (4 * H1) + q * H1 + uu)) : make_float2(0.f, 0.f);
+    const int pub_word = frag_word(bl, uu);      // units uu (even), uu + 1 are adjacent words of a fragment vector
     __syncthreads();
 
     PH_DECL
@@ -332,41 +328,38 @@ __global__ void __launch_bounds__(NT, 1) opnet_l1head_kernel(const L1HeadParams 
         PH(4);  // barrier
         {
             // ---- cells of frame i: gates, cell update, publish first, stash after ------------------------------------------
-            float hv[2], act[2][4];
+            float hv[2], act[4][2];
+            float2 dpre[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                dpre[q] = i >= 1 ? *reinterpret_cast<const float2*>(d_s + (q * 8 + bl) * DPAD + ul) : make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                float a[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) a[q] = xp[j][q] + (i >= 1 ? d_s[(q * 8 + bl[j]) * DPAD + ul[j]] : 0.0f);
-                act[j][0] = fmaf(0.5f, tanh_sfu(0.5f * a[0]), 0.5f);
-                act[j][1] = fmaf(0.5f, tanh_sfu(0.5f * a[1]), 0.5f);
-                act[j][2] = tanh_sfu(a[2]);
-                act[j][3] = fmaf(0.5f, tanh_sfu(0.5f * a[3]), 0.5f);
-                cst[j] = fmaf(act[j][1], cst[j], act[j][0] * act[j][2]);
-                hv[j] = act[j][3] * tanh_sfu(cst[j]);
-                if (valid[j]) {      // also the last frame: its head still needs h1[T-1]
-                    const uint32_t w = flagged(hv[j], step_parity(i));
-                    asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(ring + (size_t)(i & 1) * (kGroup * H1) + frag_word(bl[j], u0 + ul[j])),
-                                 "r"(w)
-                                 : "memory");
-                }
+                const float a0 = (j ? xp[0].y + dpre[0].y : xp[0].x + dpre[0].x), a1 = (j ? xp[1].y + dpre[1].y : xp[1].x + dpre[1].x);
+                const float a2 = (j ? xp[2].y + dpre[2].y : xp[2].x + dpre[2].x), a3 = (j ? xp[3].y + dpre[3].y : xp[3].x + dpre[3].x);
+                act[0][j] = fmaf(0.5f, tanh_sfu(0.5f * a0), 0.5f);
+                act[1][j] = fmaf(0.5f, tanh_sfu(0.5f * a1), 0.5f);
+                act[2][j] = tanh_sfu(a2);
+                act[3][j] = fmaf(0.5f, tanh_sfu(0.5f * a3), 0.5f);
+                cst[j] = fmaf(act[1][j], cst[j], act[0][j] * act[2][j]);
+                hv[j] = act[3][j] * tanh_sfu(cst[j]);
             }
+            if (valid) {      // also the last frame: its head still needs h1[T-1]
+                const uint32_t par = step_parity(i);
+                asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1,%2};" ::"l"(ring + (size_t)(i & 1) * (kGroup * H1) + pub_word),
+                             "r"(flagged(hv[0], par)), "r"(flagged(hv[1], par))
+                             : "memory");
+                const size_t r = row0 + i;
+                if (i + 1 < T) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (valid[j]) {
-                    const size_t r = row[j] + i;
-                    const int uu = u0 + ul[j];
-                    p.hs1[r * H1 + uu] = hv[j];
-                    if (p.gates1) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) p.gates1[r * (4 * H1) + q * H1 + uu] = act[j][q];
-                    }
-                    if (p.cells1) p.cells1[r * H1 + uu] = cst[j];
-                    if (i + 1 < T) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) xp[j][q] = __ldg(p.xproj1 + (r + 1) * (4 * H1) + q * H1 + uu);
-                    }
+                    for (int q = 0; q < 4; ++q) xp[q] = __ldg(reinterpret_cast<const float2*>(p.xproj1 + (r + 1) * (4 * H1) + q * H1 + uu));
                 }
+                *reinterpret_cast<float2*>(p.hs1 + r * H1 + uu) = make_float2(hv[0], hv[1]);
+                if (p.gates1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<float2*>(p.gates1 + r * (4 * H1) + q * H1 + uu) = make_float2(act[q][0], act[q][1]);
+                }
+                if (p.cells1) *reinterpret_cast<float2*>(p.cells1 + r * H1 + uu) = make_float2(cst[0], cst[1]);
             }
         }
         PH(5);  // cells + publish + stash
