@@ -171,6 +171,16 @@ OPN_API int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1, int64_t H2, const fl
                   const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2, const float* gates1,
                   const float* cells1, const float* gates2, const float* cells2, const float* d_hs2, float* d_gates1,
                   float* d_gates2, float* d_logits, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same in two calls.  In its default form on a B200 the backward runs as two concurrent kernels: the LSTM2 reverse loop on
+ * `stream` and the head backward + LSTM1 reverse recurrence on a library-owned side stream, which finishes ~0.15 ms later.
+ * opn_opnet_bwd_begin returns with d_gates2 ordered on `stream` but d_gates1 / d_logits still outstanding, so the caller can
+ * enqueue work that needs only d_gates2 (the weight gradients of LSTM2: opn_wgrad) on the 128 SMs that are already free;
+ * opn_opnet_bwd_join(stream) orders d_gates1 / d_logits on `stream` (a no-op when the single-kernel form ran). */
+OPN_API int opn_opnet_bwd_begin(int64_t B, int64_t T, int64_t H1, int64_t H2, const float* boxes, const float* probs,
+                  const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2, const float* gates1,
+                  const float* cells1, const float* gates2, const float* cells2, const float* d_hs2, float* d_gates1,
+                  float* d_gates2, float* d_logits, void* workspace, int64_t workspace_bytes, void* stream);
+OPN_API int opn_opnet_bwd_join(void* stream);
 
 /* ---- LSTM weight gradients -------------------------------------------------------------
  * The time-parallel contractions autograd forms for the weights of nn.LSTM (baselines/learned_models.py:39,46,76,113,

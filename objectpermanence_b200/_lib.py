@@ -46,6 +46,8 @@ SIGNATURES = {
     "opn_opnet_fwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 16 + [c_int64, _P]),
     "opn_opnet_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "opn_opnet_bwd": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 15 + [c_int64, _P]),
+    "opn_opnet_bwd_begin": (c_int, [c_int64, c_int64, c_int64, c_int64] + [_P] * 15 + [c_int64, _P]),
+    "opn_opnet_bwd_join": (c_int, [_P]),
     "opn_wgrad_workspace_bytes": (c_int64, [c_int32, POINTER(WgradJob)]),
     "opn_wgrad": (c_int, [c_int32, POINTER(WgradJob), _P, c_int64, _P]),
     "opn_attention_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),

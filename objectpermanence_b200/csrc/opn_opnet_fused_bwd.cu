@@ -678,11 +678,12 @@ extern "C" int64_t opn_opnet_bwd_workspace_bytes(int64_t B, int64_t T) {
     return (int64_t)(a > b ? a : b);
 }
 
-extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* probs,
-                             const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2,
-                             const float* gates1, const float* cells1, const float* gates2, const float* cells2,
-                             const float* dhs2, float* dgates1, float* dgates2, float* d_logits, void* workspace,
-                             int64_t workspace_bytes, void* stream) {
+// defer_join: leave the side stream un-joined (opn_opnet_bwd_begin); *pending says whether a join is outstanding
+static int opnet_bwd_impl(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* probs,
+                          const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2,
+                          const float* gates1, const float* cells1, const float* gates2, const float* cells2,
+                          const float* dhs2, float* dgates1, float* dgates2, float* d_logits, void* workspace,
+                          int64_t workspace_bytes, void* stream, bool defer_join) {
     OPN_CHECK_ARG(B > 0 && T > 0, "opnet_bwd: B and T must be positive");
     if (H1_ != H1 || H2_ != H2) {
         set_error("opnet_bwd: the fused backward exists for the shipped OPNet config (H1 = 256, H2 = 512), got %lld / %lld",
@@ -744,9 +745,34 @@ extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, con
             }
         }
         OPN_CUDA(cudaEventRecord(side->join, side->stream));
-        OPN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+        if (!defer_join) OPN_CUDA(cudaStreamWaitEvent(s, side->join, 0));
         return OPN_OK;
     }
     if (single) return launch_ring(opnet_bwd_fused_kernel<true, false>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
     return launch_ring(opnet_bwd_fused_kernel<false, false>, p, NT, NS, (size_t)SMEM_BYTES, B, s, "opnet_bwd");
+}
+
+extern "C" int opn_opnet_bwd(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* probs,
+                             const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2,
+                             const float* gates1, const float* cells1, const float* gates2, const float* cells2,
+                             const float* dhs2, float* dgates1, float* dgates2, float* d_logits, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    return opnet_bwd_impl(B, T, H1_, H2_, boxes, probs, w_hh1, w_pred, w_ih2, w_hh2, gates1, cells1, gates2, cells2, dhs2, dgates1, dgates2,
+                          d_logits, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int opn_opnet_bwd_begin(int64_t B, int64_t T, int64_t H1_, int64_t H2_, const float* boxes, const float* probs,
+                                   const float* w_hh1, const float* w_pred, const float* w_ih2, const float* w_hh2,
+                                   const float* gates1, const float* cells1, const float* gates2, const float* cells2,
+                                   const float* dhs2, float* dgates1, float* dgates2, float* d_logits, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+    return opnet_bwd_impl(B, T, H1_, H2_, boxes, probs, w_hh1, w_pred, w_ih2, w_hh2, gates1, cells1, gates2, cells2, dhs2, dgates1, dgates2,
+                          d_logits, workspace, workspace_bytes, stream, true);
+}
+
+extern "C" int opn_opnet_bwd_join(void* stream) {
+    // the join event of the side stream is recorded by every split-form call (and is complete when none was made): waiting
+    // on it is always safe, and a no-op in the single-kernel form
+    if (SideStream* side = opnet_side_stream()) OPN_CUDA(cudaStreamWaitEvent(as_stream(stream), side->join, 0));
+    return OPN_OK;
 }

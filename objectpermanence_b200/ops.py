@@ -601,15 +601,30 @@ class OPNetTrunkFn(torch.autograd.Function):
             timed = _launch_timer.bracket("opnet_bwd_fused") if _launch_timer is not None else None
             if timed:
                 timed[0].record()
-            rc = lib.opn_opnet_bwd(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
-                                   w_ih2.data_ptr(), w_hh2.data_ptr(), gates1.data_ptr(), cells1.data_ptr(),
-                                   gates2.data_ptr(), cells2.data_ptr(), dhs2.data_ptr(), dgates1.data_ptr(),
-                                   dgates2.data_ptr(), dl.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            x1 = boxes.reshape(B, T, -1)
+            early = wgrad_tc_wanted(B * T, 4 * H1) and all(need[1:6]) and os.environ.get("OPN_WGRAD_EARLY", "1") not in ("0", "")
+            entry = lib.opn_opnet_bwd_begin if early else lib.opn_opnet_bwd
+            rc = entry(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
+                       w_ih2.data_ptr(), w_hh2.data_ptr(), gates1.data_ptr(), cells1.data_ptr(),
+                       gates2.data_ptr(), cells2.data_ptr(), dhs2.data_ptr(), dgates1.data_ptr(),
+                       dgates2.data_ptr(), dl.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+            _lib.check(rc, "opn_opnet_bwd")
+            if early:
+                # The LSTM2 loop (d_gates2) finishes ~0.15 ms before the head / LSTM1 kernel beside it: its two weight gradients
+                # run on the 128 SMs it has freed while that kernel completes, then the join, then the other three products
+                j2, dw_ih2, dw_hh2 = _lstm_wgrad_jobs(dgates2, fb, hs2, w_ih2, w_hh2, True, True)
+                wgrad_jobs_run(j2)
+                _lib.check(lib.opn_opnet_bwd_join(_stream()), "opn_opnet_bwd_join")
+                if timed:
+                    timed[1].record()
+                _lstm_check(dev, "opn_opnet_bwd")
+                j1, dw_ih1, dw_hh1 = _lstm_wgrad_jobs(dgates1, x1, hs1, w_ih1, w_hh1, True, True)
+                dw_pred = _grad_like(w_pred)
+                wgrad_jobs_run(j1 + [(hs1.reshape(B * T, H1), dl.reshape(B * T, 15), dw_pred, T, 0, True)])
+                return None, dw_ih1, dw_hh1, dw_pred, dw_ih2, dw_hh2, None
             if timed:
                 timed[1].record()
-            _lib.check(rc, "opn_opnet_bwd")
             _lstm_check(dev, "opn_opnet_bwd")
-            x1 = boxes.reshape(B, T, -1)
             if wgrad_tc_wanted(B * T, 4 * H1) and all(need[1:6]):
                 # all five weight gradients as ONE launch of the tcgen05 weight-gradient kernel (+ its reduction);
                 # dW_pred in the transposed orientation (H1 = the 128-wide dimension)
