@@ -54,7 +54,7 @@ WORKLOAD = ("opnet configs/opnet_model_config.json [B=32 per GPU,T=300,N=15,F=6]
 def config_for(world: int) -> dict:
     """`config` of the JSON line: ONE definition for both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": f"dp{world}",
-            "collective": "one NCCL all-reduce of the flat fp32 gradient per step" if world > 1 else "none",
+            "collective": "NCCL all-reduce of the flat fp32 gradient, once per step in two buckets (the weights of LSTM2 start inside the backward pass)" if world > 1 else "none",
             "l2": "256 MB buffer written between timed iterations (untimed)"}
 
 

@@ -103,6 +103,16 @@ def unregister_grad_slots(params) -> None:
         _grad_slots.pop(p.data_ptr(), None)
 
 
+# Called by OPNet's backward with the gradients that are final before the rest of the backward pass has finished (the weights of
+# LSTM2): a data-parallel reducer starts their all-reduce then, in the shadow of the remaining kernels.
+_early_grads_hook = None
+
+
+def set_early_grads_hook(fn) -> None:
+    global _early_grads_hook
+    _early_grads_hook = fn
+
+
 def _grad_like(weight: torch.Tensor) -> torch.Tensor:
     """Uninitialised tensor for the gradient of `weight`: its registered flat-buffer slice, else a fresh allocation."""
     slot = _grad_slots.get(weight.data_ptr())
@@ -614,6 +624,8 @@ class OPNetTrunkFn(torch.autograd.Function):
                 # run on the 128 SMs it has freed while that kernel completes, then the join, then the other three products
                 j2, dw_ih2, dw_hh2 = _lstm_wgrad_jobs(dgates2, fb, hs2, w_ih2, w_hh2, True, True)
                 wgrad_jobs_run(j2)
+                if _early_grads_hook is not None:
+                    _early_grads_hook((dw_ih2, dw_hh2))
                 _lib.check(lib.opn_opnet_bwd_join(_stream()), "opn_opnet_bwd_join")
                 if timed:
                     timed[1].record()
