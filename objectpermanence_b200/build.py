@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libopnet_b200.so")
-SOURCES = ["opn_api.cu", "opn_lstm.cu", "opn_lstm_mma.cu", "opn_lstm_tc.cu", "opn_attention_tc.cu", "opn_wgrad_tc.cu", "opn_opnet_fused.cu", "opn_opnet_l1head.cu", "opn_opnet_fused_bwd.cu", "opn_opnet_l1bwd.cu", "opn_gemm.cu", "opn_gemm_skinny.cu", "opn_gemm_tc.cu", "opn_pointwise.cu", "opn_head_loss.cu", "opn_train_eval.cu"]
+SOURCES = ["opn_api.cu", "opn_lstm.cu", "opn_lstm_mma.cu", "opn_lstm_tc.cu", "opn_attention_tc.cu", "opn_wgrad_tc.cu", "opn_opnet_fused.cu", "opn_opnet_l1head.cu", "opn_opnet_fused_bwd.cu", "opn_opnet_l1bwd.cu", "opn_gemm.cu", "opn_gemm_skinny.cu", "opn_gemm_proj.cu", "opn_gemm_tc.cu", "opn_pointwise.cu", "opn_head_loss.cu", "opn_train_eval.cu"]
 HEADERS = [os.path.join(CSRC, "opn_common.cuh"), os.path.join(CSRC, "opn_lstm_common.cuh"), os.path.join(CSRC, "opn_mma_common.cuh"), os.path.join(CSRC, "opn_tc_common.cuh"), os.path.join(os.path.dirname(PKG), "include", "opnet_b200.h")]
 
 NVCC_FLAGS = [

@@ -19,6 +19,9 @@ int gemm_tc(int trans_a, int trans_b, long long M, long long N, long long K, flo
             const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int relu,
             void* workspace, long long workspace_bytes, cudaStream_t s);
 
+// short-K input projections (opn_gemm_proj.cu)
+int gemm_proj(bool ta, bool tb, long long M, long long N, long long K, float alpha, const float* A, long long lda,
+              const float* B, long long ldb, float beta, float* C, long long ldc, cudaStream_t s, bool* handled);
 // skinny shapes (opn_gemm_skinny.cu)
 int gemm_skinny(bool ta, bool tb, long long M, long long N, long long K, float alpha, const float* A, long long lda,
                 const float* B, long long ldb, float beta, float* C, long long ldc, cudaStream_t s, bool* handled);
@@ -241,6 +244,8 @@ extern "C" int opn_sgemm(int trans_a, int trans_b, int64_t M, int64_t N, int64_t
         bool handled = false;
         const int rc = gemm_skinny(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, s, &handled);
         if (handled || rc != OPN_OK) return rc;
+        const int rc2 = gemm_proj(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, s, &handled);
+        if (handled || rc2 != OPN_OK) return rc2;
     }
     if (K > 0 && workspace != nullptr && tc_eligible(M, N, K) &&
         workspace_bytes >= (int64_t)gemm_tc_workspace_bytes(M, N, K))

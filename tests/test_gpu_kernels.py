@@ -104,6 +104,37 @@ def test_sgemm_tensor_core_epilogue(cuda_device):
     assert (big[:, N:] == 7.0).all()
 
 
+# ---- short-K input projections (opn_gemm_proj.cu: x W_ih^T of an LSTM layer) -------------------------------
+@pytest.mark.parametrize("M,N,K,pad", [
+    (9600, 1024, 90, 0),      # OPNet LSTM1 at the headline shape (learned_models.py:29)
+    (1100, 2048, 75, 0),      # baseline_lstm: odd K (scalar loads), ragged last row tile
+    (2048, 136, 128, 2),      # ragged column tile, K at the upper end (one CTA per SM), padded leading dimensions
+    (1024, 128, 16, 0),       # smallest K
+    (4096, 512, 18, 4),       # K padded to 32 inside the kernel
+])
+def test_sgemm_short_k_projection(cuda_device, M, N, K, pad):
+    A = torch.zeros(M, K + pad); A[:, :K] = _rand((M, K), 31, 1.0)
+    W = torch.zeros(N, K + pad); W[:, :K] = _rand((N, K), 32, 1.0)
+    A[:, K:] = 5.0; W[:, K:] = 5.0            # must not be read into the product
+    C = torch.full((M, N + pad), 7.0, device=cuda_device)
+    want = A[:, :K].double() @ W[:, :K].double().t()
+    ops.sgemm(A.to(cuda_device), W.to(cuda_device), C, trans_a=False, trans_b=True, M=M, N=N, K=K, lda=K + pad,
+              ldb=K + pad, ldc=N + pad)
+    got = C.cpu()
+    assert torch.isfinite(got).all()
+    assert (got[:, :N].double() - want).abs().max().item() <= 5e-5 * want.abs().max().item()
+    assert (got[:, N:] == 7.0).all()
+    # the 1e-2 mode: one 16-bit product
+    ops.set_precision("bf16")
+    try:
+        ops.sgemm(A.to(cuda_device), W.to(cuda_device), C, trans_a=False, trans_b=True, M=M, N=N, K=K, lda=K + pad,
+                  ldb=K + pad, ldc=N + pad)
+    finally:
+        ops.set_precision("fp32")
+    err = (C.cpu()[:, :N].double() - want).abs().max().item()
+    assert err <= 1e-2 * want.abs().max().item()
+
+
 # ---- skinny contractions (rowdot / colred / tinyk fast paths and their fall-backs) ---------------------------
 @pytest.mark.parametrize("case", [
     # (ta, tb, M, N, K, lda_pad, ldb_pad, ldc_pad, alpha, beta)
