@@ -68,3 +68,68 @@ def test_reducer_single_process_is_identity():
     r = FlatGradAllReducer(lin.parameters())
     flat = r.reduce()
     assert torch.equal(flat, want) and r.collectives == 0 and r.nbytes == 4 * 8
+
+
+class _FakeWork:
+    def __init__(self, log):
+        self.log = log
+
+    def wait(self):
+        self.log.append(("wait",))
+
+
+def _stub_nccl(monkeypatch, log):
+    """dist.* as a 2-rank NCCL job would answer, with all_reduce recording the slice it was handed."""
+    monkeypatch.setattr(dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 2)
+    monkeypatch.setattr(dist, "get_backend", lambda group=None: "nccl")
+
+    def all_reduce(t, op=None, group=None, async_op=False):
+        log.append(("all_reduce", t.data_ptr(), t.numel(), bool(async_op), op))
+        return _FakeWork(log) if async_op else None
+
+    monkeypatch.setattr(dist, "all_reduce", all_reduce)
+
+
+def test_early_bucket_covers_exactly_the_final_gradients_and_reduce_covers_the_rest(monkeypatch):
+    """Host logic of the two-bucket all-reduce (OPNet: the weight gradients of LSTM2 are final inside the backward pass): the hook
+    starts ONE asynchronous all-reduce over the contiguous slice the gradients occupy, reduce() sends the two ends of the buffer
+    and then waits for the bucket; gradients that are not back-to-back slices of the buffer are left to reduce()."""
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 7, 11, 3)]
+    red = FlatGradAllReducer(params)
+    for p, v in zip(params, red._views):
+        v.fill_(1.0)
+        p.grad = v
+    log = []
+    _stub_nccl(monkeypatch, log)
+    base, esz = red.flat.data_ptr(), red.flat.element_size()
+
+    # not contiguous in the buffer (views 0 and 2): nothing starts
+    red._start_early_bucket((red._views[0], red._views[2]))
+    assert red._early is None and log == []
+    # a tensor that is not part of the buffer: nothing starts
+    red._start_early_bucket((torch.zeros(7),))
+    assert red._early is None and log == []
+
+    # views 1 and 2, handed over in any order: one async all-reduce over elements [5, 23)
+    red._start_early_bucket((red._views[2], red._views[1]))
+    assert log == [("all_reduce", base + 5 * esz, 18, True, dist.ReduceOp.AVG)]
+    assert red._early is not None and red._early[1:] == (5, 23)
+    # a second hook call in the same step does not start a second bucket
+    red._start_early_bucket((red._views[1],))
+    assert len(log) == 1
+
+    log.clear()
+    red.reduce()
+    ends = sorted((e[1], e[2]) for e in log if e[0] == "all_reduce")
+    assert ends == [(base, 5), (base + 23 * esz, 3)]          # [0, 5) and [23, 26)
+    assert all(not e[3] for e in log if e[0] == "all_reduce")
+    assert log[-1] == ("wait",) and red._early is None
+    assert red.collectives == 2                               # the bucket + the grouped ends
+    for p, v in zip(params, red._views):
+        assert p.grad.data_ptr() == v.data_ptr()
+
+    # next step without the hook firing: a single all-reduce over the whole buffer
+    log.clear()
+    red.reduce()
+    assert log == [("all_reduce", base, 26, False, dist.ReduceOp.AVG)]

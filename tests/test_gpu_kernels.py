@@ -453,6 +453,50 @@ def test_opnet_backward_two_kernel_split_equals_the_single_kernel(cuda_device, m
         assert (a - b).abs().max().item() <= 2e-6 * max(1e-6, b.abs().max().item()) + 1e-12, name
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("B,T,launches", [(8, 2000, 12), (32, 300, 40)])
+def test_opnet_exchange_is_repeatable_over_many_launches(cuda_device, monkeypatch, split, B, T, launches):
+    """Stress of the inter-CTA hand-over (flagged words through L2 read by polls and by TMA bulk copies, the producer / consumer
+    rings): a torn or stale word would change a hidden state and every frame after it, so many launches of the fused forward and
+    backward on the same inputs -- 2000 dependent frames each at config 4's shape -- must agree BIT FOR BIT with the first one, in
+    the single-kernel and in the split form, with no time-out on the status page (formal-memory-model item)."""
+    lib = _lib.load()
+    monkeypatch.setenv("OPN_OPNET_SPLIT", split)
+    H1, H2 = 256, 512
+    g = torch.Generator().manual_seed(5 * B + T)
+    r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1).to(cuda_device)
+    boxes = torch.rand(B, T, 15, 6, generator=g).to(cuda_device)
+    xproj1 = r(B, T, 4 * H1) * 0.5
+    w_hh1, w_pred, w_ih2, w_hh2 = r(4 * H1, H1) / H1 ** 0.5, r(15, H1) / H1 ** 0.5, r(4 * H2, 6) / H2 ** 0.5, r(4 * H2, H2) / H2 ** 0.5
+    dh2 = r(B, T, H2) * 0.01
+    fshapes = [(B, T, H1), (B, T, 4 * H1), (B, T, H1), (B, 15, T), (B, T, 15), (B, T, 6), (B, T, H2), (B, T, 4 * H2), (B, T, H2)]
+    bshapes = [(B, T, 4 * H1), (B, T, 4 * H2), (B, T, 15)]
+    s = torch.cuda.current_stream().cuda_stream
+    first = None
+    for it in range(launches):
+        f = [torch.full(sh, float("nan"), device=cuda_device) for sh in fshapes]
+        ws = torch.empty(lib.opn_opnet_fwd_workspace_bytes(B, T), dtype=torch.uint8, device=cuda_device)
+        _lib.check(lib.opn_opnet_fwd(B, T, H1, H2, boxes.data_ptr(), xproj1.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
+                                     w_ih2.data_ptr(), w_hh2.data_ptr(), *[o.data_ptr() for o in f], ws.data_ptr(), ws.numel(), s),
+                   "opn_opnet_fwd")
+        hs1, gates1, cells1, _, probs, _, _, gates2, cells2 = f
+        b = [torch.full(sh, float("nan"), device=cuda_device) for sh in bshapes]
+        wb = torch.empty(lib.opn_opnet_bwd_workspace_bytes(B, T), dtype=torch.uint8, device=cuda_device)
+        _lib.check(lib.opn_opnet_bwd(B, T, H1, H2, boxes.data_ptr(), probs.data_ptr(), w_hh1.data_ptr(), w_pred.data_ptr(),
+                                     w_ih2.data_ptr(), w_hh2.data_ptr(), gates1.data_ptr(), cells1.data_ptr(), gates2.data_ptr(),
+                                     cells2.data_ptr(), dh2.data_ptr(), *[o.data_ptr() for o in b], wb.data_ptr(), wb.numel(), s),
+                   "opn_opnet_bwd")
+        ops.check_status(cuda_device, "opn_opnet_fwd / opn_opnet_bwd")
+        outs = f + b
+        if first is None:
+            first = outs
+            for o in outs:
+                assert torch.isfinite(o).all()
+        else:
+            for k, (a, ref) in enumerate(zip(outs, first)):
+                assert torch.equal(a, ref), f"launch {it}: output {k} differs from the first launch"
+
+
 # ---- fused OPNet forward ----------------------------------------------------------------------
 # "fused_inline" after "fused" (two-stream weight gradients, the default) is the order in which [11-37] failed once in
 # round 1; root cause and fix: DESIGN.md section 9 (leftover shared memory read by the fused backward's first sweep)
