@@ -53,6 +53,9 @@ OPN_API int opn_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * every fp32 operand into bf16 hi+lo and accumulates hi*hi + hi*lo + lo*hi in fp32 TMEM
  * (relative operand error 2^-17).  opn_sgemm_workspace_bytes() returns the scratch size the
  * tensor-core path wants for a shape, or 0 when the FFMA kernel will be used.
+ * Short-K input projections (x * W_ih^T: trans_a == 0, trans_b != 0, 16 <= K <= 128, M >= 1024, alpha 1, beta 0, no
+ * bias / ReLU) take a third kernel that splits the fp32 operands on the way into shared memory and needs no scratch
+ * (opn_gemm_proj.cu; same bf16 hi+lo arithmetic).  Skinny shapes (one operand at most 16 wide) have their own kernels too.
  * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N], optional ReLU.
  *   trans_a == 0: A is [M,K] row-major (lda);  trans_a != 0: A is [K,M] row-major
  *   trans_b == 0: B is [K,N] row-major (ldb);  trans_b != 0: B is [N,K] row-major
